@@ -1,0 +1,156 @@
+/* jpeg2png_b200.h — C ABI of the B200-native jpeg2png solver (libjpeg2png_b200.so).
+ *
+ * Plain C, plain pointers and sizes.  Two layers:
+ *
+ *   1. The DROP-IN layer: `compute()` with exactly the signature, ownership rules and side
+ *      effects of the reference solver entry (reference compute.h:8, compute.c:407-465) and the
+ *      data contract `struct coef` (reference jpeg2png.h:7-20).  A reference build links this
+ *      library instead of its own compute.o/box.o/ooura/dct.o and nothing else changes
+ *      (see INTEGRATION.md).
+ *
+ *   2. The SESSION layer (`j2p_*`): the same solver with the device residency made explicit,
+ *      so that a caller (bench, batch driver, multi-GPU strip driver) can keep coefficient
+ *      planes resident in HBM, time the iteration loop without the host<->device copies, and
+ *      run several frames on several streams/devices.  `compute()` is implemented on top of it.
+ *
+ * There is NO CPU fallback anywhere behind this header: if no CUDA device is usable every entry
+ * point fails (drop-in layer: die() -> exit(EXIT_FAILURE) like the reference, utils.c:20-28;
+ * session layer: negative return code + j2p_last_error()).
+ */
+#ifndef JPEG2PNG_B200_H
+#define JPEG2PNG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------------------------------
+ * Data contract — layout-identical to the reference's `struct coef` (jpeg2png.h:7-20).
+ *   h, w            plane size in samples (multiples of 8; jpeg.c:52-53)
+ *   h_samp, w_samp  upsampling factors of this plane w.r.t. the frame (jpeg.c:57-58)
+ *   data            quantised DCT coefficients, int16, [blocks][64] natural order, blocks in
+ *                   raster order (jpeg.c:68-77); read-only for the solver, owned by the caller
+ *   fdata           in : conventional decode, raster h x w, 0-centred (jpeg2png.c:127-139)
+ *                   out: solver result, raster H x W of the working frame (compute.c:455-461)
+ *   quant_table     natural order, all entries non-zero (jpeg.c:41-46)
+ * ------------------------------------------------------------------------------------- */
+struct coef {
+        unsigned h;
+        unsigned w;
+        unsigned h_samp;
+        unsigned w_samp;
+        int16_t *data;
+        float *fdata;
+        uint16_t quant_table[64];
+};
+
+/* Reference logger.h:6-11 and progressbar.h:4-7: the solver writes log->iteration every
+ * iteration (compute.c:428), calls logger_log once per iteration (compute.c:271-272) and
+ * progressbar_inc once per iteration when pb != NULL (compute.c:449-452). */
+struct logger;
+struct progressbar;
+
+/* ---------------------------------------------------------------------------------------
+ * 1. Drop-in entry.  Replaces reference compute.c:407-465.
+ *
+ *   - frees coefs[c].fdata (it must come from aligned_alloc/malloc, utils.h:89-106) and replaces
+ *     it with a new 16-byte-aligned malloc-family buffer of H*W floats owned by the caller;
+ *   - overwrites coefs[c].w/h with the frame size W,H (compute.c:460-461);
+ *   - re-entrant: may be called concurrently from several host threads (jpeg2png.c:147, :330);
+ *     each call uses its own CUDA stream and no mutable global state;
+ *   - errors: message on stderr prefixed "jpeg2png: " and exit(EXIT_FAILURE) (utils.c:11-28).
+ *
+ * The callbacks are resolved at link time exactly like in the reference: the host program
+ * provides logger_log() and progressbar_inc() (reference logger.c:20-27, progressbar.c:52-54).
+ * When the library is loaded stand-alone (tests, bench) weak no-op defaults are used.
+ * ------------------------------------------------------------------------------------- */
+void compute(unsigned nchannel, struct coef *coefs, struct logger *log, struct progressbar *pb,
+             float weight, float *pweight, unsigned iterations);
+
+/* ---------------------------------------------------------------------------------------
+ * 2. Session layer.
+ * ------------------------------------------------------------------------------------- */
+typedef struct j2p_session j2p_session;
+
+enum {
+        J2P_OK = 0,
+        J2P_ERR_ARG = -1,      /* bad argument (sizes not multiples of 8, nchannel > 3, ...) */
+        J2P_ERR_CUDA = -2,     /* a CUDA runtime call failed; see j2p_last_error()           */
+        J2P_ERR_NODEVICE = -3  /* no usable sm_100 device                                    */
+};
+
+/* Thread-local text of the last failure on this host thread ("" if none). */
+const char *j2p_last_error(void);
+
+/* Number of CUDA devices visible to this process (0 if none / no driver). */
+int j2p_device_count(void);
+
+/* Describes one frame to solve: the planes that are optimised TOGETHER (reference joint mode:
+ * nchannel = 3, jpeg2png.c:144; separate mode: three sessions with nchannel = 1, :147-152).
+ * `row0`/`rows` select a horizontal strip of the frame for multi-GPU spatial tiling; pass
+ * row0 = 0, rows = 0 for the whole frame. */
+struct j2p_frame_desc {
+        unsigned nchannel;       /* 1..3 */
+        unsigned plane_w[3];     /* coef->w  */
+        unsigned plane_h[3];     /* coef->h  */
+        unsigned w_samp[3];      /* coef->w_samp */
+        unsigned h_samp[3];      /* coef->h_samp */
+        float weight;            /* TGV weight (-w), compute.c:257-260 */
+        float pweight[3];        /* DCT-distance weights (-p), compute.c:244-245 */
+        unsigned iterations;     /* total iteration count (fixes the step size, compute.c:443) */
+};
+
+/* Create a session on `device` (cudaSetDevice ordinal).  Allocates all HBM working buffers. */
+int j2p_session_create(j2p_session **out, int device, const struct j2p_frame_desc *desc);
+void j2p_session_destroy(j2p_session *s);
+
+/* Working-frame size W x H = max over planes of (plane_w*w_samp, plane_h*h_samp) (compute.c:410-416). */
+unsigned j2p_session_width(const j2p_session *s);
+unsigned j2p_session_height(const j2p_session *s);
+
+/* Host -> HBM.  `data`: int16 [blocks][64]; `quant`: uint16[64]; `fdata`: raster plane_h x plane_w
+ * conventional decode.  Performs the reference aux_init (compute.c:278-310) on the device:
+ * cos = data*quant, nearest-neighbour upsample with edge clamp, fista = fdata.  Asynchronous on
+ * the session stream when the host buffers are pinned. */
+int j2p_session_upload(j2p_session *s, unsigned channel, const int16_t *data,
+                       const uint16_t *quant, const float *fdata);
+
+/* Re-arm the iteration state from the already-resident coefficient planes and the resident copy
+ * of the conventional decode (no host traffic) — lets a benchmark time the loop repeatedly. */
+int j2p_session_reset(j2p_session *s);
+
+/* Run `n` solver iterations starting at iteration index `first` (0-based) on the session stream.
+ * Asynchronous.  The FISTA momentum sequence (compute.c:431-432) restarts when first == 0. */
+int j2p_session_iterate(j2p_session *s, unsigned first, unsigned n);
+
+/* HBM -> host: the current iterate of `channel`, H x W floats raster. */
+int j2p_session_download(j2p_session *s, unsigned channel, float *out);
+
+/* Objective terms of the most recent iteration, as logged by the reference (compute.c:271-272):
+ * out[0]=objective, out[1]=prob_dist, out[2]=tv, out[3]=tv2.  Only tracked when logging was
+ * enabled with j2p_session_set_logging(s, 1) before iterating. */
+int j2p_session_set_logging(j2p_session *s, int enabled);
+int j2p_session_objective(j2p_session *s, double out[4]);
+
+/* Block the host until everything queued on the session stream has finished. */
+int j2p_session_sync(j2p_session *s);
+
+/* Raw handles for callers that schedule their own work around the session (bench timing with
+ * CUDA events on the launching stream; torch interop).  The stream is a cudaStream_t. */
+void *j2p_session_stream(j2p_session *s);
+/* Device pointer of the current iterate of `channel` (H x W floats). */
+void *j2p_session_plane_ptr(j2p_session *s, unsigned channel);
+
+/* Launch counters: number of kernel launches issued by this session since creation. */
+unsigned long long j2p_session_launches(const j2p_session *s);
+
+/* Version string of the library build. */
+const char *j2p_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JPEG2PNG_B200_H */
