@@ -126,6 +126,11 @@ int j2p_session_reset(j2p_session *s);
  * Asynchronous.  The FISTA momentum sequence (compute.c:431-432) restarts when first == 0. */
 int j2p_session_iterate(j2p_session *s, unsigned first, unsigned n);
 
+/* Block the host until iteration `iter` (0-based, already queued by j2p_session_iterate) has
+ * finished on the device.  This is what lets `compute()` advance the reference's progress bar
+ * (compute.c:449-452) at the pace of the device without draining the stream. */
+int j2p_session_wait_iteration(j2p_session *s, unsigned iter);
+
 /* HBM -> host: the current iterate of `channel`, H x W floats raster. */
 int j2p_session_download(j2p_session *s, unsigned channel, float *out);
 

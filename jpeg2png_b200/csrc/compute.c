@@ -1,0 +1,127 @@
+/* compute.c — the drop-in solver entry, host side, C11.
+ *
+ * Same symbol, signature, ownership rules and callbacks as the reference's compute()
+ * (reference compute.h:8, compute.c:407-465); the body only marshals `struct coef` into a device
+ * session (session.cu) and back.  There is no CPU implementation of the solver behind it: when no
+ * sm_100 device is usable this dies like every other fatal error of the reference
+ * (utils.c:11-28: "jpeg2png: <message>" on stderr, exit(EXIT_FAILURE)).
+ */
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/jpeg2png_b200.h"
+
+/* Layout mirrors of the two callback structs (reference logger.h:6-11, progressbar.h:4-7); the
+ * host program owns the real definitions. */
+struct logger {
+        FILE *f;
+        const char *filename;
+        unsigned channel;
+        unsigned iteration;
+};
+struct progressbar {
+        unsigned current;
+        unsigned max;
+};
+
+/* Provided by the host program when this library replaces the reference solver objects
+ * (reference logger.c:20-27, progressbar.c:52-54, progressbar.c:56-66 + utils.c:11-17).  Weak:
+ * a stand-alone load (tests, bench) simply has no callbacks. */
+extern void logger_log(struct logger *log, double objective, double prob_dist, double tv, double tv2) __attribute__((weak));
+extern void progressbar_inc(struct progressbar *pb) __attribute__((weak));
+extern void progressbar_clear(struct progressbar *pb) __attribute__((weak));
+extern struct progressbar *main_progressbar __attribute__((weak));
+
+_Noreturn static void die(const char *msg, ...) {
+        /* utils.c:11-28 */
+        if (&main_progressbar && main_progressbar) {
+                if (progressbar_clear) progressbar_clear(main_progressbar);
+                main_progressbar = NULL;
+        }
+        fprintf(stderr, "jpeg2png: ");
+        va_list l;
+        va_start(l, msg);
+        vfprintf(stderr, msg, l);
+        va_end(l);
+        fprintf(stderr, "\n");
+        exit(EXIT_FAILURE);
+}
+
+/* how many iterations may be queued on the device ahead of the progress bar */
+#define J2P_PROGRESS_LAG 8u
+
+void compute(unsigned nchannel, struct coef *coefs, struct logger *log, struct progressbar *pb,
+             float weight, float *pweight, unsigned iterations) {
+        if (nchannel < 1 || nchannel > 3) die("compute: nchannel must be 1..3");
+
+        struct j2p_frame_desc d;
+        memset(&d, 0, sizeof d);
+        d.nchannel = nchannel;
+        d.weight = weight;
+        d.iterations = iterations;
+        for (unsigned c = 0; c < nchannel; c++) {
+                d.plane_w[c] = coefs[c].w;
+                d.plane_h[c] = coefs[c].h;
+                d.w_samp[c] = coefs[c].w_samp;
+                d.h_samp[c] = coefs[c].h_samp;
+                d.pweight[c] = pweight[c];
+        }
+
+        /* device choice: J2P_DEVICE (set by the batch / multi-GPU drivers), default 0 */
+        int device = 0;
+        const char *env = getenv("J2P_DEVICE");
+        if (env && *env) device = atoi(env);
+
+        j2p_session *s = NULL;
+        if (j2p_session_create(&s, device, &d) != J2P_OK) die("%s", j2p_last_error());
+        const int want_log = log && log->f != NULL;
+        if (want_log && j2p_session_set_logging(s, 1) != J2P_OK) die("%s", j2p_last_error());
+
+        for (unsigned c = 0; c < nchannel; c++) {
+                if (j2p_session_upload(s, c, coefs[c].data, coefs[c].quant_table, coefs[c].fdata) != J2P_OK)
+                        die("%s", j2p_last_error());
+                free(coefs[c].fdata);                                   /* compute.c:304-305 */
+                coefs[c].fdata = NULL;
+        }
+
+        unsigned reported = 0;
+        for (unsigned i = 0; i < iterations; i++) {
+                if (log) log->iteration = i;                            /* compute.c:428 */
+                if (j2p_session_iterate(s, i, 1) != J2P_OK) die("%s", j2p_last_error());
+                if (want_log) {
+                        double o[4];
+                        if (j2p_session_objective(s, o) != J2P_OK) die("%s", j2p_last_error());
+                        if (logger_log) logger_log(log, o[0], o[1], o[2], o[3]);   /* compute.c:271-272 */
+                }
+                if (pb && progressbar_inc) {                            /* compute.c:449-452 */
+                        while (reported + J2P_PROGRESS_LAG <= i) {
+                                if (j2p_session_wait_iteration(s, reported) != J2P_OK) die("%s", j2p_last_error());
+#pragma omp critical(progressbar)
+                                progressbar_inc(pb);
+                                reported++;
+                        }
+                }
+        }
+        if (pb && progressbar_inc) {
+                for (; reported < iterations; reported++) {
+                        if (j2p_session_wait_iteration(s, reported) != J2P_OK) die("%s", j2p_last_error());
+#pragma omp critical(progressbar)
+                        progressbar_inc(pb);
+                }
+        }
+
+        const unsigned w = j2p_session_width(s), h = j2p_session_height(s);
+        for (unsigned c = 0; c < nchannel; c++) {                       /* compute.c:455-463 */
+                size_t bytes = (size_t)w * h * sizeof(float);
+                bytes = (bytes + 15) & ~(size_t)15;
+                float *out = aligned_alloc(16, bytes);                  /* utils.h:89-98 */
+                if (!out) die("allocation error");
+                if (j2p_session_download(s, c, out) != J2P_OK) die("%s", j2p_last_error());
+                coefs[c].fdata = out;
+                coefs[c].w = w;
+                coefs[c].h = h;
+        }
+        j2p_session_destroy(s);
+}

@@ -1,0 +1,39 @@
+// kernels.cuh — device-side parameter blocks shared by kernels.cu and session.cu.
+#pragma once
+#include <stdint.h>
+
+namespace j2p {
+
+// One colour plane as the kernels see it.
+struct PlaneDev {
+    float *x;             // current iterate x_k, H x W raster              (reference aux.fdata)
+    float *xp;            // previous iterate x_{k-1}; receives x_{k+1}     (reference aux.fista)
+    float *g;             // objective sub-gradient, H x W raster           (reference aux.obj_gradient)
+    float *gp;            // DCT-distance gradient for the NEXT step at coefficient resolution,
+                          // ch x cw raster: p_alpha * idct((cos - data*q)/q^2)   (compute.c:38-70)
+    const int16_t *data;  // quantised coefficients, [blocks][64] natural order
+    int cw, ch;           // coefficient grid in samples
+    int sw, sh;           // upsampling factors
+    int resample;         // !(cw == W && ch == H)                          (compute.c:338)
+    int use_prob;         // pweight != 0                                   (compute.c:244)
+    float p_alpha;        // pweight*2*255*sqrtf(2)                         (compute.c:245)
+    float cnt;            // (float)(sw*sh), the divisor of the block mean     (compute.c:359)
+};
+
+struct FrameDev {
+    int W, H, nc;
+    PlaneDev pl[3];
+    float q[3][64];       // quantisation tables as float
+    float qq[3][64];      // q*q (fp32 product, compute.c:49)
+    float a1;             // (float)(1./sqrtf(nc))                          (compute.c:90)
+    float a2;             // (float)(alpha*1./sqrtf(nc)), alpha = weight/sqrtf(2)   (compute.c:154,258)
+    int use_tgv;          // weight != 0                                    (compute.c:257)
+    float step;           // radius / sqrtf(1 + iterations)                 (compute.c:425,443)
+    double *partials;     // [3][grad_ctas] per-CTA sums of g^2
+    float *norms;         // [3] sqrtf((float)sum g^2)                      (compute.c:200-206)
+    unsigned *counter;    // CTAs-done ticket for the last-CTA reduction
+    double *log_acc;      // [4][grad_ctas] optional objective partials (tv, tv2) + [3][proj] prob
+    int grad_ctas;
+};
+
+}  // namespace j2p

@@ -1,0 +1,327 @@
+// session.cu — host side of the solver: HBM residency, the iteration loop, the C ABI.
+//
+// Implements the `j2p_*` session layer of include/jpeg2png_b200.h.  One session = one frame (or
+// one strip of a frame) on one device with its own CUDA stream; sessions share no mutable state,
+// so `compute()` built on top of them is re-entrant like the reference (jpeg2png.c:147, :330).
+//
+// HBM layout per plane c (W x H = working frame, cw x ch = coefficient grid):
+//   x, xp   H*W fp32   iterate x_k and x_{k-1}; k_project overwrites xp with x_{k+1}, then the
+//                      two pointers swap (reference SWAP at compute.c:438)
+//   g       H*W fp32   sub-gradient
+//   gp      ch*cw fp32 DCT-distance gradient for the next step, coefficient resolution
+//   data    ch*cw i16  quantised coefficients (read-only)
+//   fdata0  ch*cw fp32 conventional decode (kept so a session can be re-armed without host I/O)
+// plus per session: partials [3][grad_ctas] fp64, norms [3] fp32, one ticket counter.
+#include <cuda_runtime.h>
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "../../include/jpeg2png_b200.h"
+#include "kernels.cuh"
+
+namespace j2p {
+int grad_cta_count(int W, int H);
+cudaError_t configure_kernels();
+cudaError_t launch_gradient(const FrameDev &F, float factor, cudaStream_t s);
+cudaError_t launch_project(const FrameDev &F, float factor, cudaStream_t s);
+cudaError_t launch_decode(const int16_t *data, const float *q_dev, float *out, int cw, int ch, cudaStream_t s);
+cudaError_t launch_init_plane(const float *fdata, float *x, float *xp, int W, int H, int cw, int ch, int sw, int sh,
+                              cudaStream_t s);
+}  // namespace j2p
+
+using namespace j2p;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(J2P_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr int kEventRing = 32;
+
+struct j2p_session {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    FrameDev F{};
+    j2p_frame_desc desc{};
+    float *x[3] = {}, *xp[3] = {}, *g[3] = {}, *gp[3] = {}, *fdata0[3] = {}, *qdev[3] = {};
+    int16_t *data[3] = {};
+    bool uploaded[3] = {};
+    float t = 1.f;            // FISTA momentum state (compute.c:426)
+    unsigned next_iter = 0;
+    unsigned long long launches = 0;
+    int logging = 0;
+    cudaEvent_t ev[kEventRing] = {};
+    long long ev_iter[kEventRing];
+};
+
+static std::once_flag g_cfg_once[64];
+static cudaError_t g_cfg_err[64];
+
+extern "C" const char *j2p_last_error(void) { return g_err; }
+
+extern "C" const char *j2p_version(void) { return "jpeg2png_b200 0.1 (sm_100a)"; }
+
+extern "C" int j2p_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" unsigned j2p_session_width(const j2p_session *s) { return s ? (unsigned)s->F.W : 0; }
+extern "C" unsigned j2p_session_height(const j2p_session *s) { return s ? (unsigned)s->F.H : 0; }
+extern "C" void *j2p_session_stream(j2p_session *s) { return s ? (void *)s->stream : nullptr; }
+extern "C" void *j2p_session_plane_ptr(j2p_session *s, unsigned c) { return (s && c < (unsigned)s->F.nc) ? s->F.pl[c].x : nullptr; }
+extern "C" unsigned long long j2p_session_launches(const j2p_session *s) { return s ? s->launches : 0; }
+
+extern "C" void j2p_session_destroy(j2p_session *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (int c = 0; c < 3; c++) {
+        cudaFree(s->x[c]); cudaFree(s->xp[c]); cudaFree(s->g[c]); cudaFree(s->gp[c]);
+        cudaFree(s->fdata0[c]); cudaFree(s->qdev[c]); cudaFree(s->data[c]);
+    }
+    cudaFree(s->F.partials); cudaFree(s->F.norms); cudaFree(s->F.counter);
+    for (int i = 0; i < kEventRing; i++)
+        if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+static int create_impl(j2p_session *s, int device, const j2p_frame_desc *d) {
+    const int ndev = j2p_device_count();
+    if (ndev <= 0) return fail(J2P_ERR_NODEVICE, "no CUDA device available (the solver has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(J2P_ERR_ARG, "device %d out of range (0..%d)", device, ndev - 1);
+    if (d->nchannel < 1 || d->nchannel > 3) return fail(J2P_ERR_ARG, "nchannel must be 1..3 (compute.c:118)");
+    s->device = device;
+    s->desc = *d;
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(J2P_ERR_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    if (device < 64) {
+        std::call_once(g_cfg_once[device], [&] { g_cfg_err[device] = configure_kernels(); });
+        CK(g_cfg_err[device]);
+    } else {
+        CK(configure_kernels());
+    }
+
+    FrameDev &F = s->F;
+    F.nc = (int)d->nchannel;
+    unsigned W = 0, H = 0;
+    for (unsigned c = 0; c < d->nchannel; c++) {                       // compute.c:410-416
+        if (d->plane_w[c] == 0 || d->plane_h[c] == 0 || (d->plane_w[c] & 7) || (d->plane_h[c] & 7))
+            return fail(J2P_ERR_ARG, "plane %u size %ux%u is not a positive multiple of 8", c, d->plane_w[c], d->plane_h[c]);
+        if (d->w_samp[c] < 1 || d->h_samp[c] < 1) return fail(J2P_ERR_ARG, "plane %u has a zero sampling factor", c);
+        if (d->plane_w[c] * d->w_samp[c] > W) W = d->plane_w[c] * d->w_samp[c];
+        if (d->plane_h[c] * d->h_samp[c] > H) H = d->plane_h[c] * d->h_samp[c];
+    }
+    if ((unsigned long long)W * H > 0x7fffffffull) return fail(J2P_ERR_ARG, "frame %ux%u too large", W, H);
+    F.W = (int)W;
+    F.H = (int)H;
+    const size_t n = (size_t)W * H;
+
+    // scalars, evaluated on the host in the reference's own float expressions
+    const float radius = sqrtf((float)H * (float)W) / 2;                // compute.c:425
+    F.step = radius / sqrtf((float)(1 + d->iterations));                // compute.c:443
+    F.a1 = (float)(1. / (double)sqrtf((float)d->nchannel));             // compute.c:90
+    const float tgv_alpha = d->weight / sqrtf((float)(4 / 2));          // compute.c:258
+    F.a2 = (float)(((double)tgv_alpha * 1.) / (double)sqrtf((float)d->nchannel));   // compute.c:154
+    F.use_tgv = d->weight != 0.f;                                       // compute.c:257
+
+    CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < kEventRing; i++) {
+        CK(cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming));
+        s->ev_iter[i] = -1;
+    }
+    for (unsigned c = 0; c < d->nchannel; c++) {
+        PlaneDev &P = F.pl[c];
+        P.cw = (int)d->plane_w[c]; P.ch = (int)d->plane_h[c];
+        P.sw = (int)d->w_samp[c]; P.sh = (int)d->h_samp[c];
+        P.resample = !(d->plane_w[c] == W && d->plane_h[c] == H);       // compute.c:338
+        P.use_prob = d->pweight[c] != 0.f;                              // compute.c:244
+        P.p_alpha = d->pweight[c] * 2 * 255 * sqrtf(2);                 // compute.c:245
+        P.cnt = (float)(d->w_samp[c] * d->h_samp[c]);                   // compute.c:359
+        const size_t nc = (size_t)P.cw * P.ch;
+        CK(cudaMalloc(&s->x[c], n * sizeof(float)));
+        CK(cudaMalloc(&s->xp[c], n * sizeof(float)));
+        CK(cudaMalloc(&s->g[c], n * sizeof(float)));
+        CK(cudaMalloc(&s->gp[c], nc * sizeof(float)));
+        CK(cudaMalloc(&s->fdata0[c], nc * sizeof(float)));
+        CK(cudaMalloc(&s->data[c], nc * sizeof(int16_t)));
+        CK(cudaMalloc(&s->qdev[c], 64 * sizeof(float)));
+        P.x = s->x[c]; P.xp = s->xp[c]; P.g = s->g[c]; P.gp = s->gp[c]; P.data = s->data[c];
+    }
+    F.grad_ctas = grad_cta_count(F.W, F.H);
+    CK(cudaMalloc(&F.partials, sizeof(double) * 3 * (size_t)F.grad_ctas));
+    CK(cudaMalloc(&F.norms, sizeof(float) * 4));
+    CK(cudaMalloc(&F.counter, sizeof(unsigned)));
+    CK(cudaMemsetAsync(F.counter, 0, sizeof(unsigned), s->stream));
+    CK(cudaMemsetAsync(F.norms, 0, sizeof(float) * 4, s->stream));
+    return J2P_OK;
+}
+
+extern "C" int j2p_session_create(j2p_session **out, int device, const struct j2p_frame_desc *d) {
+    if (!out || !d) return fail(J2P_ERR_ARG, "null argument");
+    *out = nullptr;
+    j2p_session *s = new j2p_session();
+    const int rc = create_impl(s, device, d);
+    if (rc != J2P_OK) {
+        char keep[sizeof g_err];
+        memcpy(keep, g_err, sizeof keep);
+        j2p_session_destroy(s);
+        cudaGetLastError();
+        memcpy(g_err, keep, sizeof keep);
+        return rc;
+    }
+    *out = s;
+    return J2P_OK;
+}
+
+static int reset_impl(j2p_session *s) {
+    FrameDev &F = s->F;
+    for (int c = 0; c < F.nc; c++) {
+        if (!s->uploaded[c]) return fail(J2P_ERR_ARG, "plane %d has not been uploaded", c);
+        PlaneDev &P = F.pl[c];
+        P.x = s->x[c];
+        P.xp = s->xp[c];
+        CK(launch_init_plane(s->fdata0[c], P.x, P.xp, F.W, F.H, P.cw, P.ch, P.sw, P.sh, s->stream));
+        s->launches++;
+        // first step: cos == data*q exactly, so the DCT-distance gradient is exactly 0 (compute.c:283 vs :47)
+        CK(cudaMemsetAsync(P.gp, 0, (size_t)P.cw * P.ch * sizeof(float), s->stream));
+    }
+    s->t = 1.f;
+    s->next_iter = 0;
+    return J2P_OK;
+}
+
+extern "C" int j2p_session_reset(j2p_session *s) {
+    if (!s) return fail(J2P_ERR_ARG, "null session");
+    CK(cudaSetDevice(s->device));
+    return reset_impl(s);
+}
+
+extern "C" int j2p_session_upload(j2p_session *s, unsigned c, const int16_t *data, const uint16_t *quant,
+                                  const float *fdata) {
+    if (!s || !data || !quant) return fail(J2P_ERR_ARG, "null argument");
+    if (c >= (unsigned)s->F.nc) return fail(J2P_ERR_ARG, "channel %u out of range", c);
+    CK(cudaSetDevice(s->device));
+    FrameDev &F = s->F;
+    PlaneDev &P = F.pl[c];
+    const size_t nc = (size_t)P.cw * P.ch;
+    float qf[64];
+    for (int j = 0; j < 64; j++) {
+        if (quant[j] == 0) return fail(J2P_ERR_ARG, "invalid quantization table (zero entry, jpeg.c:41-45)");
+        qf[j] = (float)quant[j];
+        F.q[c][j] = qf[j];
+        F.qq[c][j] = qf[j] * qf[j];                                     // fp32 product (compute.c:49)
+    }
+    CK(cudaMemcpyAsync(s->qdev[c], qf, sizeof qf, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemcpyAsync(s->data[c], data, nc * sizeof(int16_t), cudaMemcpyHostToDevice, s->stream));
+    if (fdata) {
+        CK(cudaMemcpyAsync(s->fdata0[c], fdata, nc * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    } else {
+        CK(launch_decode(s->data[c], s->qdev[c], s->fdata0[c], P.cw, P.ch, s->stream));
+        s->launches++;
+    }
+    // qf lives on this stack frame: make sure the (pageable, hence already staged) copy is done
+    CK(cudaStreamSynchronize(s->stream));
+    s->uploaded[c] = true;
+    bool all = true;
+    for (int k = 0; k < F.nc; k++) all = all && s->uploaded[k];
+    if (all) return reset_impl(s);
+    return J2P_OK;
+}
+
+extern "C" int j2p_session_iterate(j2p_session *s, unsigned first, unsigned n) {
+    if (!s) return fail(J2P_ERR_ARG, "null session");
+    CK(cudaSetDevice(s->device));
+    FrameDev &F = s->F;
+    for (int c = 0; c < F.nc; c++)
+        if (!s->uploaded[c]) return fail(J2P_ERR_ARG, "plane %d has not been uploaded", c);
+    if (first == 0 && s->next_iter != 0) {
+        const int rc = reset_impl(s);
+        if (rc != J2P_OK) return rc;
+    }
+    if (first != s->next_iter) return fail(J2P_ERR_ARG, "iterations must be contiguous (expected %u, got %u)", s->next_iter, first);
+    for (unsigned i = first; i < first + n; i++) {
+        // FISTA momentum (compute.c:431-432, :440), host floats
+        const float tnext = (1 + sqrtf(1 + 4 * (s->t * s->t))) / 2;
+        const float factor = (s->t - 1) / tnext;
+        s->t = tnext;
+        CK(launch_gradient(F, factor, s->stream));
+        CK(launch_project(F, factor, s->stream));
+        s->launches += 2;
+        for (int c = 0; c < F.nc; c++) {                                // compute.c:438
+            float *tmp = F.pl[c].x;
+            F.pl[c].x = F.pl[c].xp;
+            F.pl[c].xp = tmp;
+        }
+        const int slot = (int)(i % kEventRing);
+        CK(cudaEventRecord(s->ev[slot], s->stream));
+        s->ev_iter[slot] = (long long)i;
+    }
+    s->next_iter = first + n;
+    return J2P_OK;
+}
+
+extern "C" int j2p_session_wait_iteration(j2p_session *s, unsigned iter) {
+    if (!s) return fail(J2P_ERR_ARG, "null session");
+    CK(cudaSetDevice(s->device));
+    const int slot = (int)(iter % kEventRing);
+    if (s->ev_iter[slot] == (long long)iter) {
+        CK(cudaEventSynchronize(s->ev[slot]));
+    } else if (iter >= s->next_iter) {
+        return fail(J2P_ERR_ARG, "iteration %u has not been queued", iter);
+    }   // else: its slot was recycled, so it finished long ago
+    return J2P_OK;
+}
+
+extern "C" int j2p_session_download(j2p_session *s, unsigned c, float *out) {
+    if (!s || !out) return fail(J2P_ERR_ARG, "null argument");
+    if (c >= (unsigned)s->F.nc) return fail(J2P_ERR_ARG, "channel %u out of range", c);
+    CK(cudaSetDevice(s->device));
+    const size_t n = (size_t)s->F.W * s->F.H;
+    CK(cudaMemcpyAsync(out, s->F.pl[c].x, n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return J2P_OK;
+}
+
+extern "C" int j2p_session_sync(j2p_session *s) {
+    if (!s) return fail(J2P_ERR_ARG, "null session");
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    return J2P_OK;
+}
+
+extern "C" int j2p_session_set_logging(j2p_session *s, int enabled) {
+    if (!s) return fail(J2P_ERR_ARG, "null session");
+    s->logging = enabled != 0;
+    return J2P_OK;
+}
+
+extern "C" int j2p_session_objective(j2p_session *s, double out[4]) {
+    if (!s || !out) return fail(J2P_ERR_ARG, "null argument");
+    return fail(J2P_ERR_ARG, "objective logging is not implemented yet");
+}

@@ -1,0 +1,141 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI of
+libjpeg2png_b200.so and is compared BIT FOR BIT with the oracle restatement, with the committed
+golden vectors (produced by the unmodified reference), and — when the prebuilt oracle/_ref
+travelled with the snapshot — with the compiled reference itself."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from jpeg2png_b200 import abi, synth
+from tests import helpers as H
+from tests.golden_io import golden_cases, load_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def lib():
+    lib = abi.load_product()
+    assert lib.j2p_device_count() > 0, 'no CUDA device visible: the product has no CPU fallback'
+    return lib
+
+
+def _checker():
+    """Reference build if it travelled, else the oracle restatement (pinned to it by test_oracle)."""
+    return 'ref' if H.have_ref() else 'oracle'
+
+
+@pytest.mark.parametrize('name', golden_cases())
+def test_product_matches_golden(lib, name):
+    g = load_case(name)
+    out = H.run_compute('product', g['img'], g['channels'], g['weight'], g['pweight'], g['iterations'], g['fdata'])
+    H.assert_bit_identical(out, g['out'], f'golden {name}')
+
+
+@pytest.mark.parametrize('w,h,q,ss,channels,weight,pw,iters', [
+    (256, 256, 10, '4:2:0', [0, 1, 2], 0.3, [0.001] * 3, 50),      # BASELINE config 1
+    (256, 256, 10, '4:2:0', [0], 0.3, [0.001], 50),                # separate mode (-s), luma
+    (256, 256, 10, '4:2:0', [1], 0.3, [0.001], 50),                # separate mode (-s), chroma (resample)
+    (200, 120, 30, '4:2:0', [0, 1, 2], 0.3, [0.001] * 3, 30),      # frame larger than the luma grid
+    (136, 72, 50, '4:4:4', [0, 1, 2], 0.7, [0.001, 0.0, 0.01], 40),
+    (64, 64, 90, '4:4:4', [0, 1, 2], 0.0, [0.0] * 3, 20),          # TV only
+    (520, 264, 75, '4:2:0', [0, 1, 2], 0.3, [0.001] * 3, 25),      # several CTAs in both directions, ragged edges
+])
+def test_product_matches_oracle(lib, w, h, q, ss, channels, weight, pw, iters):
+    img = synth.synth_coefs(w, h, q, ss, seed=1234 + w + h)
+    f = H.decode_planes(img, channels)
+    want = H.run_compute(_checker(), img, channels, weight, pw, iters, f)
+    got = H.run_compute('product', img, channels, weight, pw, iters, f)
+    H.assert_bit_identical(got, want, 'product vs checker')
+
+
+def test_product_matches_oracle_random_planes(lib):
+    for seed in range(4):
+        img = synth.random_coefs([(40, 24), (24, 16), (16, 8)], [(1, 1), (2, 2), (3, 4)], seed)
+        f = H.decode_planes(img)
+        want = H.run_compute(_checker(), img, [0, 1, 2], 0.4, [0.001] * 3, 12, f)
+        got = H.run_compute('product', img, [0, 1, 2], 0.4, [0.001] * 3, 12, f)
+        H.assert_bit_identical(got, want, f'random seed {seed}')
+
+
+def test_config2_1080p_420_full_length(lib):
+    """BASELINE config 2: 1920x1080 Q10 4:2:0, -i 100, all three planes.  Frame 1920x1088, luma
+    grid 1080 rows (SURVEY headline 4).  Checked against the compiled reference when present
+    (about 15 s of host time), else against the oracle."""
+    img = synth.synth_coefs(1920, 1080, 10, '4:2:0', seed=1236)
+    assert (img.frame_w, img.frame_h) == (1920, 1088) and img.planes[0].h == 1080
+    f = H.decode_planes(img)
+    want = H.run_compute(_checker(), img, [0, 1, 2], 0.3, [0.001] * 3, 100, f)
+    got = H.run_compute('product', img, [0, 1, 2], 0.3, [0.001] * 3, 100, f)
+    H.assert_bit_identical(got, want, 'config 2')
+
+
+def test_device_decode_matches_oracle(lib):
+    """j2p_session_upload(fdata=NULL) runs the conventional decode on the device (jpeg.c:83-92)."""
+    img = synth.synth_coefs(104, 72, 35, '4:2:0', seed=77)
+    want = H.decode_planes(img)
+    d = abi.FrameDesc()
+    d.nchannel = 3
+    for c, p in enumerate(img.planes):
+        d.plane_w[c], d.plane_h[c], d.w_samp[c], d.h_samp[c] = p.w, p.h, p.w_samp, p.h_samp
+        d.pweight[c] = 0.001
+    d.weight = 0.3
+    d.iterations = 0
+    s = C.c_void_p()
+    assert lib.j2p_session_create(C.byref(s), 0, C.byref(d)) == 0, lib.j2p_last_error()
+    try:
+        for c, p in enumerate(img.planes):
+            data = np.ascontiguousarray(p.data)
+            quant = np.ascontiguousarray(p.quant)
+            assert lib.j2p_session_upload(s, c, data.ctypes.data, quant.ctypes.data, None) == 0, lib.j2p_last_error()
+        W, H_ = lib.j2p_session_width(s), lib.j2p_session_height(s)
+        for c, p in enumerate(img.planes):
+            out = np.empty((H_, W), np.float32)
+            assert lib.j2p_session_download(s, c, out.ctypes.data) == 0
+            # aux_init upsampling of the decode (compute.c:295-302)
+            yy = np.minimum(np.arange(H_) // p.h_samp, p.h - 1)
+            xx = np.minimum(np.arange(W) // p.w_samp, p.w - 1)
+            exp = want[c][yy][:, xx]
+            assert (H.bits(out) == H.bits(exp)).all()
+    finally:
+        lib.j2p_session_destroy(s)
+
+
+def test_session_reset_is_reproducible(lib):
+    """Re-arming a resident session and re-running gives the same bits (run-to-run determinism of
+    the fixed-order fp64 reduction)."""
+    img = synth.synth_coefs(300, 200, 20, '4:2:0', seed=5)
+    f = H.decode_planes(img)
+    d = abi.FrameDesc()
+    d.nchannel = 3
+    for c, p in enumerate(img.planes):
+        d.plane_w[c], d.plane_h[c], d.w_samp[c], d.h_samp[c] = p.w, p.h, p.w_samp, p.h_samp
+        d.pweight[c] = 0.001
+    d.weight = 0.3
+    d.iterations = 30
+    s = C.c_void_p()
+    assert lib.j2p_session_create(C.byref(s), 0, C.byref(d)) == 0, lib.j2p_last_error()
+    try:
+        for c, p in enumerate(img.planes):
+            data = np.ascontiguousarray(p.data)
+            quant = np.ascontiguousarray(p.quant)
+            fd = np.ascontiguousarray(f[c])
+            assert lib.j2p_session_upload(s, c, data.ctypes.data, quant.ctypes.data, fd.ctypes.data) == 0
+        W, H_ = lib.j2p_session_width(s), lib.j2p_session_height(s)
+        runs = []
+        for _ in range(3):
+            assert lib.j2p_session_iterate(s, 0, 30) == 0, lib.j2p_last_error()
+            planes = []
+            for c in range(3):
+                out = np.empty((H_, W), np.float32)
+                assert lib.j2p_session_download(s, c, out.ctypes.data) == 0
+                planes.append(out)
+            runs.append(planes)
+        H.assert_bit_identical(runs[0], runs[1], 'rerun 1')
+        H.assert_bit_identical(runs[0], runs[2], 'rerun 2')
+        want = H.run_compute('oracle', img, [0, 1, 2], 0.3, [0.001] * 3, 30, f)
+        H.assert_bit_identical(runs[0], want, 'session vs oracle')
+    finally:
+        lib.j2p_session_destroy(s)
