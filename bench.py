@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the jpeg2png solver hot path on B200.
+
+Workload (BASELINE.json metric, configs[2]): one 3840x2160 Q50 4:4:4 frame, all three planes
+optimised jointly, `-i 100 -w 0.3 -p 0.001` (reference defaults).  A *step* is one complete solve
+of one frame = 100 solver iterations = 200 kernel launches.  Metric: Mpixel-iterations/s =
+image_w * image_h * iterations / t / 1e6, whole job over all N GPUs.
+
+  value     solve with the coefficient planes ALREADY resident in HBM (session layer); the timed
+            region includes re-arming the iterate (reference aux_init) but no host traffic.
+  e2e       the same solve through the drop-in `compute()` with HOST `struct coef` buffers
+            (malloc-family memory, as the reference contract requires): H2D of data + quant +
+            conventional decode, 100 iterations, D2H of the three result planes, all timed.
+  roofline  the dominant kernel's ALGORITHMIC bytes per launch / its mean launch duration measured
+            live with CUDA events on the session stream (j2p_session_profile), against the
+            measured HBM copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline  the unmodified reference compute() (oracle/_ref, SSE2+OpenMP build) — or the
+            oracle port where that is absent — timed on this box's host cores on a bounded sample.
+
+N > 1 (torchrun): the path shards by independent frames (reference jpeg2png.c:330 file loop,
+BASELINE config 5 style): every rank solves its own frame on its own GPU, no data-path
+collective; NCCL is only used for the barrier and the max-over-ranks of the device time.
+Scaling is therefore "weak".
+
+`--impl reference` times the reference CPU implementation instead (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WIDTH, HEIGHT, QUALITY, SUBSAMPLING, ITERATIONS = 3840, 2160, 50, '4:4:4', 100
+WEIGHT, PWEIGHT = 0.3, 0.001
+SEED = 1234 + 3
+WORKLOAD = '3840x2160 Q50 4:4:4 synthetic JPEG coefficients, joint 3 planes, -i 100 -w 0.3 -p 0.001'
+METRIC = 'Mpixel-iterations/s'
+FALLBACK_HBM_GBS = 6650.0
+
+
+def algorithmic_bytes(img, nchannel=3):
+    """Bytes one launch of each kernel must move, per frame.
+
+    Per plane-pixel with s = w_samp*h_samp:
+      k_gradient: read x_k 4 + x_{k-1} 4 + gp 4/s, write g 4                      = 12 + 4/s
+      k_project : read x_k 4 + x_{k-1} 4 + g 4 + data 2/s, write x_{k+1} 4 + gp 4/s = 16 + 6/s
+    (SURVEY.md §8d's two-pass figure is 28 + 12/s; this design needs 28 + 10/s because the
+    DCT-distance gradient is produced inside k_project and k_gradient never reads `data`.)
+    """
+    n = img.frame_w * img.frame_h
+    grad = proj = 0.0
+    for p in img.planes[:nchannel]:
+        s = p.w_samp * p.h_samp
+        cover = (p.w * p.h) / (n / s) if n else 1.0      # planes whose grid is smaller than the frame
+        grad += n * 12 + n / s * 4 * cover
+        proj += n * 16 + n / s * 6 * cover
+    return grad, proj
+
+
+def sample_clocks(stop, out, device):
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+    q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    try:
+        p = subprocess.Popen(['nvidia-smi', f'--id={device}', f'--query-gpu={q}', '--format=csv,noheader,nounits', '-lms', '100'],
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    except OSError:
+        return
+
+    def reader():
+        for line in p.stdout:
+            out.append(line.strip())
+    t = threading.Thread(target=reader, daemon=True)
+    t.start()
+    stop.wait()
+    p.terminate()
+    try:
+        p.wait(timeout=2)
+    except Exception:
+        p.kill()
+
+
+def summarise_clocks(lines):
+    sm, mx, reasons = [], [], set()
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    for ln in lines:
+        f = [x.strip() for x in ln.split(',')]
+        if len(f) < 7:
+            continue
+        try:
+            sm.append(float(f[0]))
+            mx.append(float(f[1]))
+        except ValueError:
+            continue
+        for name, v in zip(names, f[3:7]):
+            if v.lower().startswith('active'):
+                reasons.add(name)
+    if not sm:
+        return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+    busy = sorted(sm)[len(sm) // 2:]           # upper half = samples taken under load
+    return {'sm_mhz': float(np.median(busy)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return FALLBACK_HBM_GBS, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def recorded_traffic(kernel):
+    """dram bytes per launch from the committed ncu --set full capture (profiles/), or None."""
+    path = os.path.join(ROOT, 'profiles', 'traffic.json')
+    try:
+        with open(path) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
+def make_frame(seed):
+    from jpeg2png_b200 import synth
+    return synth.synth_coefs(WIDTH, HEIGHT, QUALITY, SUBSAMPLING, seed)
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline
+# ---------------------------------------------------------------------------------------------
+def cpu_solve_rate(img, fdata, iterations, kind):
+    """Time ONE compute() call of `iterations` iterations with the CPU checker (host marshalling
+    excluded); returns (Mpix-it/s, seconds)."""
+    from tests import helpers as H
+    timer = {}
+    H.run_compute(kind, img, [0, 1, 2], WEIGHT, [PWEIGHT] * 3, iterations, fdata, timer=timer)
+    dt = timer['seconds']
+    return img.width * img.height * iterations / dt / 1e6, dt
+
+
+def cpu_kind_and_cores():
+    from tests import helpers as H
+    if H.have_ref():
+        lib = H.load_ref()
+        return 'ref', 'reference', int(lib.ref_glue_max_threads())
+    H.build_oracle_libs()
+    return 'oracle', 'port', os.cpu_count() or 1
+
+
+def cpu_warmup(kind):
+    """OpenMP cold start (about 1 s on first use) must not land in a timed call."""
+    from jpeg2png_b200 import synth
+    from tests import helpers as H
+    small = synth.synth_coefs(64, 64, 50, '4:4:4', 1)
+    H.run_compute(kind, small, [0, 1, 2], WEIGHT, [PWEIGHT] * 3, 2)
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    kind, label, cores = cpu_kind_and_cores()
+    img = make_frame(SEED)
+    cpu_warmup(kind)
+    # bounded sample: per-iteration cost does not depend on the iteration count, so every step
+    # solves the same frame for `it` iterations, sized so the whole run stays within ~3 minutes
+    budget_s = 150.0
+    per_iter_s = 0.65
+    it = int(max(1, min(ITERATIONS, budget_s / ((args.steps + args.warmup) * per_iter_s))))
+    from tests import helpers as H
+    fdata = H.decode_planes(img)
+    for _ in range(args.warmup):
+        cpu_solve_rate(img, fdata, it, kind)
+    dt = 0.0
+    for _ in range(args.steps):
+        dt += cpu_solve_rate(img, fdata, it, kind)[1]
+    value = img.width * img.height * it * args.steps / dt / 1e6
+    sample = f'{WIDTH}x{HEIGHT} 4:4:4 frame, {it} of {ITERATIONS} iterations per step (per-iteration cost is iteration-count independent)'
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'Mpix-it/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': 'Mpix-it/s', 'cores': cores, 'kind': label, 'sample': sample},
+        'e2e': {'value': value, 'unit': 'Mpix-it/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# product arm
+# ---------------------------------------------------------------------------------------------
+def run_product_arm(args, rank, local_rank, world):
+    import torch
+    from jpeg2png_b200 import abi
+
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py: no CUDA device; the solver has no CPU path to fall back to')
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    lib = abi.load_product()
+
+    img = make_frame(SEED + rank)               # every rank solves its own frame
+    W, H = img.frame_w, img.frame_h
+
+    def barrier():
+        if dist is not None:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- resident session -------------------------------------------------------------------
+    d = abi.FrameDesc()
+    d.nchannel = 3
+    for c, p in enumerate(img.planes):
+        d.plane_w[c], d.plane_h[c], d.w_samp[c], d.h_samp[c] = p.w, p.h, p.w_samp, p.h_samp
+        d.pweight[c] = PWEIGHT
+    d.weight = WEIGHT
+    d.iterations = ITERATIONS
+    s = C.c_void_p()
+    if lib.j2p_session_create(C.byref(s), local_rank, C.byref(d)) != 0:
+        raise RuntimeError(lib.j2p_last_error().decode())
+    for c, p in enumerate(img.planes):
+        data = np.ascontiguousarray(p.data)
+        quant = np.ascontiguousarray(p.quant)
+        # fdata = NULL: the conventional decode runs on the device (jpeg.c:83-92 restated in k_decode)
+        if lib.j2p_session_upload(s, c, data.ctypes.data, quant.ctypes.data, None) != 0:
+            raise RuntimeError(lib.j2p_last_error().decode())
+    stream = torch.cuda.ExternalStream(lib.j2p_session_stream(s), device=torch.device('cuda', local_rank))
+
+    def solve_resident():
+        if lib.j2p_session_iterate(s, 0, ITERATIONS) != 0:
+            raise RuntimeError(lib.j2p_last_error().decode())
+
+    for _ in range(max(args.warmup, 3)):
+        solve_resident()
+    lib.j2p_session_sync(s)
+
+    clock_lines, stop = [], threading.Event()
+    sampler = None
+    if rank == 0:
+        sampler = threading.Thread(target=sample_clocks, args=(stop, clock_lines, local_rank), daemon=True)
+        sampler.start()
+        time.sleep(0.3)
+
+    launches0 = lib.j2p_session_launches(s)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        solve_resident()
+    ev1.record(stream)
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = int(lib.j2p_session_launches(s) - launches0)
+
+    # ---- per-kernel live timing for the roofline (rank 0, N=1 semantics: one GPU's kernels) ----
+    mg, mp = C.c_float(), C.c_float()
+    if lib.j2p_session_profile(s, 20, C.byref(mg), C.byref(mp)) != 0:
+        raise RuntimeError(lib.j2p_last_error().decode())
+    lib.j2p_session_sync(s)
+
+    # result checksum of the resident solve (kept out of the timed region)
+    solve_resident()
+    out = np.empty((H, W), np.float32)
+    lib.j2p_session_download(s, 0, out.ctypes.data)
+    checksum = float(np.float64(out).sum())
+    lib.j2p_session_destroy(s)
+
+    # ---- end to end through compute() with host buffers --------------------------------------
+    # the conventional decode the caller of compute() owns (jpeg2png.c:127-139): produced once,
+    # outside the timed region, by the product's own device decode
+    fdata = device_decode(lib, img, local_rank)
+    h2d = sum(p.data.nbytes + p.quant.nbytes + p.w * p.h * 4 for p in img.planes)
+    d2h = 3 * W * H * 4
+    n_e2e = args.steps
+    arrays = [abi.CoefArray(img, [0, 1, 2], fdata) for _ in range(n_e2e + 1)]
+    pw = (C.c_float * 3)(PWEIGHT, PWEIGHT, PWEIGHT)
+    lg = abi.Logger(None, b'', 3, 0)
+    os.environ['J2P_DEVICE'] = str(local_rank)
+    lib.compute(3, arrays[0].arr, C.byref(lg), None, C.c_float(WEIGHT), pw, ITERATIONS)     # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(n_e2e):
+        lib.compute(3, arrays[1 + k].arr, C.byref(lg), None, C.c_float(WEIGHT), pw, ITERATIONS)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_checksum = float(np.float64(arrays[1].result(0)).sum())
+    for a in arrays:
+        a.release()
+
+    if sampler is not None:
+        stop.set()
+        sampler.join(timeout=3)
+
+    if rank == 0:
+        pix_it = WIDTH * HEIGHT * ITERATIONS
+        value = world * pix_it * args.steps / (ms_total * 1e-3) / 1e6
+        e2e_value = world * pix_it * n_e2e / e2e_s / 1e6
+        peak, peak_src = measured_peak()
+        gb, pb = algorithmic_bytes(img)
+        kernels = [
+            {'name': 'k_gradient', 'ms': float(mg.value), 'bytes': gb},
+            {'name': 'k_project', 'ms': float(mp.value), 'bytes': pb},
+        ]
+        for k in kernels:
+            k['gbs'] = k['bytes'] / (k['ms'] * 1e-3) / 1e9
+            k['frac'] = k['gbs'] / peak
+            k['traffic'] = recorded_traffic(k['name'])
+        dom = max(kernels, key=lambda k: k['ms'])
+        roofline = {'bound': 'hbm', 'kernel': dom['name'], 'achieved': dom['gbs'], 'peak': peak, 'unit': 'GB/s',
+                    'frac': dom['frac'], 'traffic': dom['traffic'], 'peak_source': peak_src,
+                    'algorithmic_bytes_per_launch': dom['bytes'], 'ms_per_launch': dom['ms'],
+                    'kernels': kernels,
+                    'iteration': {'bytes': gb + pb, 'ms': float(mg.value + mp.value),
+                                  'gbs': (gb + pb) / ((mg.value + mp.value) * 1e-3) / 1e9,
+                                  'frac': (gb + pb) / ((mg.value + mp.value) * 1e-3) / 1e9 / peak}}
+        cpu = None
+        if world == 1:
+            kind, label, cores = cpu_kind_and_cores()
+            cpu_warmup(kind)
+            sample_it = 20
+            rate, secs = cpu_solve_rate(img, fdata, sample_it, kind)
+            cpu = {'value': rate, 'unit': 'Mpix-it/s', 'cores': cores, 'kind': label,
+                   'sample': f'{WIDTH}x{HEIGHT} 4:4:4 joint, {sample_it} of {ITERATIONS} iterations, one call, {secs:.1f} s '
+                             '(joint mode threads over the 3 planes only; TV/TGV passes are serial, compute.c:233,253,260)'}
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'Mpix-it/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'frames_per_step': world, 'sharding': 'one frame per GPU, no data-path collective',
+                       'l2': 'working set ~0.75 GB per frame >> 126 MB L2 (no flush needed)',
+                       'frame': [W, H], 'iterations': ITERATIONS},
+            'clocks': summarise_clocks(clock_lines),
+            'e2e': {'value': e2e_value, 'unit': 'Mpix-it/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                    'ms_per_step': e2e_s / n_e2e * 1e3, 'host_memory': 'pageable malloc-family buffers (reference struct coef contract)',
+                    'api': 'compute(3, coefs, log, NULL, 0.3, pweights, 100) via libjpeg2png_b200.so'},
+            'gpu_launches': launches,
+            'roofline': roofline,
+            'cpu_baseline': cpu,
+            'checksum': {'resident': checksum, 'e2e': e2e_checksum},
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def device_decode(lib, img, device):
+    """Conventional decode of all planes on the device (session upload with fdata=NULL, 0 iterations)."""
+    from jpeg2png_b200 import abi
+    planes = []
+    for c, p in enumerate(img.planes):
+        d = abi.FrameDesc()
+        d.nchannel = 1
+        d.plane_w[0], d.plane_h[0], d.w_samp[0], d.h_samp[0] = p.w, p.h, 1, 1
+        d.iterations = 0
+        s = C.c_void_p()
+        if lib.j2p_session_create(C.byref(s), device, C.byref(d)) != 0:
+            raise RuntimeError(lib.j2p_last_error().decode())
+        data = np.ascontiguousarray(p.data)
+        quant = np.ascontiguousarray(p.quant)
+        if lib.j2p_session_upload(s, 0, data.ctypes.data, quant.ctypes.data, None) != 0:
+            raise RuntimeError(lib.j2p_last_error().decode())
+        out = np.empty((p.h, p.w), np.float32)
+        lib.j2p_session_download(s, 0, out.ctypes.data)
+        lib.j2p_session_destroy(s)
+        planes.append(out)
+    return planes
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    if args.impl == 'reference':
+        run_reference_arm(args, rank, world)
+    else:
+        run_product_arm(args, rank, local_rank, world)
+
+
+if __name__ == '__main__':
+    main()

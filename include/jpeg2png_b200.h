@@ -126,6 +126,11 @@ int j2p_session_reset(j2p_session *s);
  * Asynchronous.  The FISTA momentum sequence (compute.c:431-432) restarts when first == 0. */
 int j2p_session_iterate(j2p_session *s, unsigned first, unsigned n);
 
+/* Measurement aid: runs `n` iterations from a freshly re-armed state with CUDA events recorded
+ * on the session stream around each kernel, and returns the mean device time per launch of the
+ * gradient kernel and of the step+projection kernel (milliseconds). */
+int j2p_session_profile(j2p_session *s, unsigned n, float *ms_gradient, float *ms_project);
+
 /* Block the host until iteration `iter` (0-based, already queued by j2p_session_iterate) has
  * finished on the device.  This is what lets `compute()` advance the reference's progress bar
  * (compute.c:449-452) at the pace of the device without draining the stream. */

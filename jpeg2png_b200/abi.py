@@ -137,6 +137,8 @@ def declare_product(lib: C.CDLL) -> C.CDLL:
     lib.j2p_session_reset.argtypes = [vp]
     lib.j2p_session_iterate.restype = C.c_int
     lib.j2p_session_iterate.argtypes = [vp, C.c_uint, C.c_uint]
+    lib.j2p_session_profile.restype = C.c_int
+    lib.j2p_session_profile.argtypes = [vp, C.c_uint, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.j2p_session_wait_iteration.restype = C.c_int
     lib.j2p_session_wait_iteration.argtypes = [vp, C.c_uint]
     lib.j2p_session_download.restype = C.c_int
@@ -162,7 +164,7 @@ def declare_product(lib: C.CDLL) -> C.CDLL:
 HEADER_SYMBOLS = [
     'compute', 'j2p_last_error', 'j2p_device_count', 'j2p_session_create', 'j2p_session_destroy',
     'j2p_session_width', 'j2p_session_height', 'j2p_session_upload', 'j2p_session_reset',
-    'j2p_session_iterate', 'j2p_session_wait_iteration', 'j2p_session_download', 'j2p_session_set_logging',
+    'j2p_session_iterate', 'j2p_session_profile', 'j2p_session_wait_iteration', 'j2p_session_download', 'j2p_session_set_logging',
     'j2p_session_objective', 'j2p_session_sync', 'j2p_session_stream', 'j2p_session_plane_ptr',
     'j2p_session_launches', 'j2p_version',
 ]

@@ -254,35 +254,76 @@ extern "C" int j2p_session_upload(j2p_session *s, unsigned c, const int16_t *dat
     return J2P_OK;
 }
 
-extern "C" int j2p_session_iterate(j2p_session *s, unsigned first, unsigned n) {
-    if (!s) return fail(J2P_ERR_ARG, "null session");
-    CK(cudaSetDevice(s->device));
+// one solver iteration on the session stream; optional events around each kernel
+static int one_iteration(j2p_session *s, cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t e2) {
     FrameDev &F = s->F;
-    for (int c = 0; c < F.nc; c++)
+    // FISTA momentum (compute.c:431-432, :440), host floats
+    const float tnext = (1 + sqrtf(1 + 4 * (s->t * s->t))) / 2;
+    const float factor = (s->t - 1) / tnext;
+    s->t = tnext;
+    if (e0) CK(cudaEventRecord(e0, s->stream));
+    CK(launch_gradient(F, factor, s->stream));
+    if (e1) CK(cudaEventRecord(e1, s->stream));
+    CK(launch_project(F, factor, s->stream));
+    if (e2) CK(cudaEventRecord(e2, s->stream));
+    s->launches += 2;
+    for (int c = 0; c < F.nc; c++) {                                    // compute.c:438
+        float *tmp = F.pl[c].x;
+        F.pl[c].x = F.pl[c].xp;
+        F.pl[c].xp = tmp;
+    }
+    return J2P_OK;
+}
+
+static int check_ready(j2p_session *s, unsigned first) {
+    for (int c = 0; c < s->F.nc; c++)
         if (!s->uploaded[c]) return fail(J2P_ERR_ARG, "plane %d has not been uploaded", c);
     if (first == 0 && s->next_iter != 0) {
         const int rc = reset_impl(s);
         if (rc != J2P_OK) return rc;
     }
     if (first != s->next_iter) return fail(J2P_ERR_ARG, "iterations must be contiguous (expected %u, got %u)", s->next_iter, first);
+    return J2P_OK;
+}
+
+extern "C" int j2p_session_iterate(j2p_session *s, unsigned first, unsigned n) {
+    if (!s) return fail(J2P_ERR_ARG, "null session");
+    CK(cudaSetDevice(s->device));
+    int rc = check_ready(s, first);
+    if (rc != J2P_OK) return rc;
     for (unsigned i = first; i < first + n; i++) {
-        // FISTA momentum (compute.c:431-432, :440), host floats
-        const float tnext = (1 + sqrtf(1 + 4 * (s->t * s->t))) / 2;
-        const float factor = (s->t - 1) / tnext;
-        s->t = tnext;
-        CK(launch_gradient(F, factor, s->stream));
-        CK(launch_project(F, factor, s->stream));
-        s->launches += 2;
-        for (int c = 0; c < F.nc; c++) {                                // compute.c:438
-            float *tmp = F.pl[c].x;
-            F.pl[c].x = F.pl[c].xp;
-            F.pl[c].xp = tmp;
-        }
+        rc = one_iteration(s, nullptr, nullptr, nullptr);
+        if (rc != J2P_OK) return rc;
         const int slot = (int)(i % kEventRing);
         CK(cudaEventRecord(s->ev[slot], s->stream));
         s->ev_iter[slot] = (long long)i;
     }
     s->next_iter = first + n;
+    return J2P_OK;
+}
+
+extern "C" int j2p_session_profile(j2p_session *s, unsigned n, float *ms_gradient, float *ms_project) {
+    if (!s || !ms_gradient || !ms_project || n == 0) return fail(J2P_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(s->device));
+    int rc = check_ready(s, 0);
+    if (rc != J2P_OK) return rc;
+    cudaEvent_t e[3];
+    for (int k = 0; k < 3; k++) CK(cudaEventCreate(&e[k]));
+    double sg = 0., sp = 0.;
+    for (unsigned i = 0; i < n; i++) {
+        rc = one_iteration(s, e[0], e[1], e[2]);
+        if (rc != J2P_OK) return rc;
+        CK(cudaEventSynchronize(e[2]));
+        float a = 0.f, b = 0.f;
+        CK(cudaEventElapsedTime(&a, e[0], e[1]));
+        CK(cudaEventElapsedTime(&b, e[1], e[2]));
+        sg += a;
+        sp += b;
+    }
+    for (int k = 0; k < 3; k++) cudaEventDestroy(e[k]);
+    s->next_iter = n;
+    *ms_gradient = (float)(sg / n);
+    *ms_project = (float)(sp / n);
     return J2P_OK;
 }
 

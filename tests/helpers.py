@@ -83,7 +83,7 @@ def _pw(pweight, n):
 
 
 def run_compute(kind: str, img: CoefImage, channels, weight, pweight, iterations, fdata=None,
-                want_log=False):
+                want_log=False, timer=None):
     """Run one `compute()`-shaped solve on planes `channels` of img.
 
     kind: 'ref' (SIMD reference build), 'ref_c' (scalar reference build), 'oracle', 'product'.
@@ -97,6 +97,8 @@ def run_compute(kind: str, img: CoefImage, channels, weight, pweight, iterations
     n = len(channels)
     pw = _pw(list(pweight), n)
     log = None
+    import time as _time
+    t0 = _time.perf_counter()
     if kind in ('ref', 'ref_c'):
         lib = load_ref(simd=(kind == 'ref'))
         lg = abi.Logger(None, b'', 0, 0)
@@ -113,6 +115,8 @@ def run_compute(kind: str, img: CoefImage, channels, weight, pweight, iterations
         lib.compute(n, ca.arr, C.byref(lg), None, C.c_float(weight), pw, iterations)
     else:
         raise ValueError(kind)
+    if timer is not None:
+        timer['seconds'] = _time.perf_counter() - t0      # the compute() call only
     out = [ca.result(k).copy() for k in range(n)]
     ca.release()
     return (out, log) if want_log else out
