@@ -36,173 +36,272 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ------------------------------------------------------------------------------------------
-// k_gradient (v1: one CTA = 32x16 frame pixels, all channels; three smem-staged passes)
+// k_gradient — register-marching, warp-autonomous stencil.
+//
+// A warp owns a vertical strip of 64 frame columns (60 target columns + a 2-column halo on each
+// side), two adjacent columns per lane, and walks down a band of rows.  All three stages of the
+// sub-gradient live in registers; horizontal neighbours are exchanged with warp shuffles (eight
+// per channel and row), vertical neighbours are the values the lane itself produced one and two
+// rows earlier.  No shared memory, no block barrier in the main loop.
+//
+// Row pipeline at step i (the FISTA point of row i has just been formed):
+//   source row s = i-1 : forward differences, joint TV norm and the three TV quotients
+//                        (compute.c:73-113); backward differences of the differences, joint TGV
+//                        norm and the four TGV quotients (compute.c:128-186)
+//   target row s-1     : receives its last two addends (below-left, below) and is stored
+//   target row s       : receives its first nine addends, in the one order that reproduces the
+//                        reference's scan-order scatter
 // ------------------------------------------------------------------------------------------
-constexpr int G_TW = 32, G_TH = 16, G_NT = 256;
-constexpr int G_YW = G_TW + 4, G_YH = G_TH + 4;   // FISTA point, halo 2
-constexpr int G_SW = G_TW + 2, G_SH = G_TH + 2;   // per-source terms, halo 1
+constexpr int GM_WARPS = 4, GM_NT = GM_WARPS * 32, GM_USE = 60;
+
+// the seven quotients of one source pixel and channel, exact division (rare fallback path)
+struct SrcTerms {
+    float tvs, tvr, tvb, t2s, lr, ud, dg;
+};
 
 template <int NC>
-__global__ void __launch_bounds__(G_NT) k_gradient(const __grid_constant__ FrameDev F, const float factor) {
-    extern __shared__ float smem[];
-    float *sy = smem;                                    // [NC][G_YH][G_YW]
-    float *st = smem + NC * G_YH * G_YW;                 // [7][NC][G_SH][G_SW]
-    constexpr int TS = G_SH * G_SW;                      // one term plane
-    float *tvs = st, *tvr = st + NC * TS, *tvb = st + 2 * NC * TS;
-    float *t2s = st + 3 * NC * TS, *t2lr = st + 4 * NC * TS, *t2ud = st + 5 * NC * TS, *t2dg = st + 6 * NC * TS;
-
-    const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * G_TW, y0 = blockIdx.y * G_TH;
+__global__ void __launch_bounds__(GM_NT) k_gradient(const __grid_constant__ FrameDev F, const float factor, const int band_rows) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int W = F.W, H = F.H;
+    const int X0 = (blockIdx.x * GM_WARPS + wid) * GM_USE;   // first target column of this warp
+    const int yb = blockIdx.y * band_rows;                   // first target row of this CTA
+    const int ye = min(yb + band_rows, H);
+    const int px0 = X0 - 2 + 2 * lane;                       // even; W is even => the pair is in or out together
+    const bool pair_in = px0 >= 0 && px0 < W;
+    const bool is_target = pair_in && lane >= 1 && lane <= 30;
+    const bool has_l0 = px0 > 0, has_r1 = px0 + 1 < W - 1;   // k=1 always has a left neighbour, k=0 a right one
+    const float a1 = F.a1, a2 = F.a2;
+    const bool use_tgv = F.use_tgv != 0;
 
-    // pass 1: FISTA point on the tile + halo 2 (0 outside the frame; never used there)
-    for (int i = tid; i < G_YW * G_YH; i += G_NT) {
-        const int ly = i / G_YW, lx = i - ly * G_YW;
-        const int px = x0 - 2 + lx, py = y0 - 2 + ly;
-        const bool in = px >= 0 && px < W && py >= 0 && py < H;
-        const size_t gi = (size_t)py * W + px;
+    double acc[NC];
+    float yP[NC][2], gxP[NC][2], gyP[NC][2], ogp[NC][2], sv_tvb[NC][2], sv_ud[NC][2], sv_dg[NC][2];
 #pragma unroll
-        for (int c = 0; c < NC; c++) {
-            float v = 0.f;
-            if (in) {
-                const float a = F.pl[c].x[gi], b = F.pl[c].xp[gi];
-                v = fadd(a, fmul(factor, fsub(a, b)));
-            }
-            sy[c * G_YH * G_YW + i] = v;
-        }
+    for (int c = 0; c < NC; c++) {
+        acc[c] = 0.;
+#pragma unroll
+        for (int k = 0; k < 2; k++) yP[c][k] = gxP[c][k] = gyP[c][k] = ogp[c][k] = sv_tvb[c][k] = sv_ud[c][k] = sv_dg[c][k] = 0.f;
     }
-    __syncthreads();
+    // coefficient-grid column of each of the two pixels (DCT-distance term is stored at coefficient resolution)
+    int gpx[NC][2];
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int cx = (px0 + k) / F.pl[c].sw;
+            gpx[c][k] = (F.pl[c].use_prob && pair_in && cx < F.pl[c].cw) ? cx : -1;
+        }
 
-    // pass 2: per-source TV / TGV terms on the tile + halo 1
-    for (int i = tid; i < TS; i += G_NT) {
-        const int ly = i / G_SW, lx = i - ly * G_SW;
-        const int px = x0 - 1 + lx, py = y0 - 1 + ly;
-        const bool in = px >= 0 && px < W && py >= 0 && py < H;
-        float o_tvs[NC], o_tvr[NC], o_tvb[NC], o_t2s[NC], o_lr[NC], o_ud[NC], o_dg[NC];
-#pragma unroll
-        for (int c = 0; c < NC; c++) o_tvs[c] = o_tvr[c] = o_tvb[c] = o_t2s[c] = o_lr[c] = o_ud[c] = o_dg[c] = 0.f;
-        if (in) {
-            const bool has_r = px < W - 1, has_d = py < H - 1, has_l = px > 0, has_u = py > 0;
-            const int yi = (ly + 1) * G_YW + (lx + 1);          // same pixel inside sy
-            float gx[NC], gy[NC], gxx[NC], gyy[NC], sym[NC];
-            float n1 = 0.f, n2 = 0.f;
-#pragma unroll
-            for (int c = 0; c < NC; c++) {
-                const float *Y = sy + c * G_YH * G_YW;
-                const float y00 = Y[yi];
-                // forward differences at this pixel (compute.c:79-81)
-                gx[c] = has_r ? fsub(Y[yi + 1], y00) : 0.f;
-                gy[c] = has_d ? fsub(Y[yi + G_YW], y00) : 0.f;
-                n1 = fadd(n1, fsq(gx[c]));
-                n1 = fadd(n1, fsq(gy[c]));
-                // forward differences at the left and upper neighbours, then backward
-                // differences of those (compute.c:136-145)
-                float gx_l = 0.f, gy_l = 0.f, gx_u = 0.f, gy_u = 0.f;
-                if (has_l) {
-                    const float yl = Y[yi - 1];
-                    gx_l = fsub(y00, yl);                                   // x-1 < W-1 always
-                    gy_l = has_d ? fsub(Y[yi - 1 + G_YW], yl) : 0.f;
-                }
-                if (has_u) {
-                    const float yu = Y[yi - G_YW];
-                    gx_u = has_r ? fsub(Y[yi - G_YW + 1], yu) : 0.f;
-                    gy_u = fsub(y00, yu);                                   // y-1 < H-1 always
-                }
-                gxx[c] = has_l ? fsub(gx[c], gx_l) : 0.f;
-                const float gyx = has_l ? fsub(gy[c], gy_l) : 0.f;
-                const float gxy = has_u ? fsub(gx[c], gx_u) : 0.f;
-                gyy[c] = has_u ? fsub(gy[c], gy_u) : 0.f;
-                sym[c] = fmul(fadd(gxy, gyx), 0.5f);                        // (gxy+gyx)/2., exact either way
-                n2 = fadd(n2, fadd(fadd(fsq(gxx[c]), fmul(2.f, fsq(sym[c]))), fsq(gyy[c])));
-            }
-            n1 = fsqrt(n1);
-            if (n1 != 0.f) {
+    if (X0 < W) {
+        for (int i = yb - 2; i <= ye + 1; i++) {
+            // ---- FISTA point of row i (compute.c:436) ------------------------------------------
+            float yN[NC][2];
+            {
+                const bool ld = pair_in && i >= 0 && i < H;
+                const size_t gi = (size_t)(ld ? i : 0) * W + (ld ? px0 : 0);
 #pragma unroll
                 for (int c = 0; c < NC; c++) {
-                    o_tvs[c] = fdiv(fmul(F.a1, -fadd(gx[c], gy[c])), n1);   // compute.c:98
-                    o_tvr[c] = fdiv(fmul(F.a1, gx[c]), n1);                 // compute.c:100
-                    o_tvb[c] = fdiv(fmul(F.a1, gy[c]), n1);                 // compute.c:103
+                    float2 a = make_float2(0.f, 0.f), b = a;
+                    if (ld) {
+                        a = *reinterpret_cast<const float2 *>(F.pl[c].x + gi);
+                        b = *reinterpret_cast<const float2 *>(F.pl[c].xp + gi);
+                    }
+                    yN[c][0] = fadd(a.x, fmul(factor, fsub(a.x, b.x)));
+                    yN[c][1] = fadd(a.y, fmul(factor, fsub(a.y, b.y)));
                 }
             }
-            if (F.use_tgv) {
-                n2 = fsqrt(n2);
-                if (n2 != 0.f) {
+            if (i >= yb - 1) {
+                const int s = i - 1;
+                const bool src_in = pair_in && s >= 0 && s < H;
+                const bool has_d = s < H - 1, has_u = s > 0;
+
+                // ---- source row s: TV (compute.c:79-105) ---------------------------------------
+                float gx0[NC][2], gy0[NC][2], tvs0[NC][2], tvr0[NC][2], tvb0[NC][2];
+                float n1[2] = {0.f, 0.f};
 #pragma unroll
-                    for (int c = 0; c < NC; c++) {
-                        const float tw = fadd(fadd(fmul(2.f, gxx[c]), fmul(2.f, sym[c])), fmul(2.f, gyy[c]));
-                        o_t2s[c] = fmul(F.a2, fdiv(-tw, n2));                            // compute.c:165
-                        o_lr[c] = fmul(F.a2, fdiv(fadd(sym[c], gxx[c]), n2));            // compute.c:167,170
-                        o_ud[c] = fmul(F.a2, fdiv(fadd(gyy[c], sym[c]), n2));            // compute.c:173,176
-                        o_dg[c] = fmul(F.a2, fdiv(-sym[c], n2));                         // compute.c:179,182
+                for (int c = 0; c < NC; c++) {
+                    const float yr1 = __shfl_down_sync(0xffffffffu, yP[c][0], 1);
+                    gx0[c][0] = fsub(yP[c][1], yP[c][0]);                         // px0 < W-1 whenever the pair is in the frame
+                    gx0[c][1] = has_r1 ? fsub(yr1, yP[c][1]) : 0.f;
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        gy0[c][k] = has_d ? fsub(yN[c][k], yP[c][k]) : 0.f;
+                        n1[k] = fadd(n1[k], fsq(gx0[c][k]));
+                        n1[k] = fadd(n1[k], fsq(gy0[c][k]));
                     }
                 }
-            }
-        }
 #pragma unroll
-        for (int c = 0; c < NC; c++) {
-            tvs[c * TS + i] = o_tvs[c];
-            tvr[c * TS + i] = o_tvr[c];
-            tvb[c * TS + i] = o_tvb[c];
-            t2s[c * TS + i] = o_t2s[c];
-            t2lr[c * TS + i] = o_lr[c];
-            t2ud[c * TS + i] = o_ud[c];
-            t2dg[c * TS + i] = o_dg[c];
-        }
-    }
-    __syncthreads();
+                for (int k = 0; k < 2; k++) {
+                    const float n = fsqrt(n1[k]);
+                    const bool live = src_in && n != 0.f;                         // compute.c:97
+                    const float y = __frcp_rn(n);
+                    bool ok = qdiv_divisor_ok(n);
+#pragma unroll
+                    for (int c = 0; c < NC; c++) {
+                        tvs0[c][k] = qdiv_fast(fmul(a1, -fadd(gx0[c][k], gy0[c][k])), n, y, ok);   // compute.c:98
+                        tvr0[c][k] = qdiv_fast(fmul(a1, gx0[c][k]), n, y, ok);                     // compute.c:100
+                        tvb0[c][k] = qdiv_fast(fmul(a1, gy0[c][k]), n, y, ok);                     // compute.c:103
+                    }
+                    if (live && !ok) {
+#pragma unroll
+                        for (int c = 0; c < NC; c++) {
+                            tvs0[c][k] = fdiv(fmul(a1, -fadd(gx0[c][k], gy0[c][k])), n);
+                            tvr0[c][k] = fdiv(fmul(a1, gx0[c][k]), n);
+                            tvb0[c][k] = fdiv(fmul(a1, gy0[c][k]), n);
+                        }
+                    }
+                    if (!live) {
+#pragma unroll
+                        for (int c = 0; c < NC; c++) tvs0[c][k] = tvr0[c][k] = tvb0[c][k] = 0.f;
+                    }
+                }
 
-    // pass 3: ordered gather into g, and the fp64 sums of squares
-    double acc[NC];
+                // ---- source row s: second-order TGV (compute.c:136-183) ------------------------
+                float t2s0[NC][2], lr0[NC][2], ud0[NC][2], dg0[NC][2];
+                if (use_tgv && i >= yb) {
+                    float gxx[NC][2], gyy[NC][2], sym[NC][2];
+                    float n2[2] = {0.f, 0.f};
 #pragma unroll
-    for (int c = 0; c < NC; c++) acc[c] = 0.;
-    for (int i = tid; i < G_TW * G_TH; i += G_NT) {
-        const int ly = i / G_TW, lx = i - ly * G_TW;
-        const int px = x0 + lx, py = y0 + ly;
-        if (px < W && py < H) {
-            const int si = (ly + 1) * G_SW + (lx + 1);
-            const size_t gi = (size_t)py * W + px;
+                    for (int c = 0; c < NC; c++) {
+                        const float gxl = __shfl_up_sync(0xffffffffu, gx0[c][1], 1);
+                        const float gyl = __shfl_up_sync(0xffffffffu, gy0[c][1], 1);
+#pragma unroll
+                        for (int k = 0; k < 2; k++) {
+                            const bool has_l = k ? true : has_l0;
+                            const float gx_l = k ? gx0[c][0] : gxl, gy_l = k ? gy0[c][0] : gyl;
+                            gxx[c][k] = has_l ? fsub(gx0[c][k], gx_l) : 0.f;
+                            const float gyx = has_l ? fsub(gy0[c][k], gy_l) : 0.f;
+                            const float gxy = has_u ? fsub(gx0[c][k], gxP[c][k]) : 0.f;
+                            gyy[c][k] = has_u ? fsub(gy0[c][k], gyP[c][k]) : 0.f;
+                            sym[c][k] = fmul(fadd(gxy, gyx), 0.5f);               // (gxy+gyx)/2., exact either way
+                            n2[k] = fadd(n2[k], fadd(fadd(fsq(gxx[c][k]), fmul(2.f, fsq(sym[c][k]))), fsq(gyy[c][k])));
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        const float n = fsqrt(n2[k]);
+                        const bool live = src_in && n != 0.f;                     // compute.c:158
+                        const float y = __frcp_rn(n);
+                        bool ok = qdiv_divisor_ok(n);
+                        float num_s[NC], num_lr[NC], num_ud[NC], num_dg[NC];
+#pragma unroll
+                        for (int c = 0; c < NC; c++) {
+                            num_s[c] = -fadd(fadd(fmul(2.f, gxx[c][k]), fmul(2.f, sym[c][k])), fmul(2.f, gyy[c][k]));
+                            num_lr[c] = fadd(sym[c][k], gxx[c][k]);
+                            num_ud[c] = fadd(gyy[c][k], sym[c][k]);
+                            num_dg[c] = -sym[c][k];
+                            t2s0[c][k] = qdiv_fast(num_s[c], n, y, ok);
+                            lr0[c][k] = qdiv_fast(num_lr[c], n, y, ok);
+                            ud0[c][k] = qdiv_fast(num_ud[c], n, y, ok);
+                            dg0[c][k] = qdiv_fast(num_dg[c], n, y, ok);
+                        }
+                        if (live && !ok) {
+#pragma unroll
+                            for (int c = 0; c < NC; c++) {
+                                t2s0[c][k] = fdiv(num_s[c], n);
+                                lr0[c][k] = fdiv(num_lr[c], n);
+                                ud0[c][k] = fdiv(num_ud[c], n);
+                                dg0[c][k] = fdiv(num_dg[c], n);
+                            }
+                        }
+#pragma unroll
+                        for (int c = 0; c < NC; c++) {
+                            t2s0[c][k] = live ? fmul(a2, t2s0[c][k]) : 0.f;       // compute.c:165
+                            lr0[c][k] = live ? fmul(a2, lr0[c][k]) : 0.f;         // compute.c:167,170
+                            ud0[c][k] = live ? fmul(a2, ud0[c][k]) : 0.f;         // compute.c:173,176
+                            dg0[c][k] = live ? fmul(a2, dg0[c][k]) : 0.f;         // compute.c:179,182
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < NC; c++)
+#pragma unroll
+                        for (int k = 0; k < 2; k++) t2s0[c][k] = lr0[c][k] = ud0[c][k] = dg0[c][k] = 0.f;
+                }
+
+                // ---- target row s-1: last two addends, store, sum of squares -------------------
+                if (i >= yb + 2) {
+                    const size_t gi = (size_t)(s - 1) * W + (is_target ? px0 : 0);
+#pragma unroll
+                    for (int c = 0; c < NC; c++) {
+                        float o0 = ogp[c][0], o1 = ogp[c][1];
+                        if (use_tgv) {
+                            const float dgl = __shfl_up_sync(0xffffffffu, dg0[c][1], 1);
+                            o0 = fadd(fadd(o0, dgl), ud0[c][0]);                  // below-left, below
+                            o1 = fadd(fadd(o1, dg0[c][0]), ud0[c][1]);
+                        }
+                        if (is_target) {
+                            *reinterpret_cast<float2 *>(F.pl[c].g + gi) = make_float2(o0, o1);
+                            acc[c] = __dadd_rn(acc[c], (double)fsq(o0));          // compute.c:203
+                            acc[c] = __dadd_rn(acc[c], (double)fsq(o1));
+                        }
+                    }
+                }
+
+                // ---- target row s: first nine addends ------------------------------------------
+                if (s >= yb && s < ye) {
+#pragma unroll
+                    for (int c = 0; c < NC; c++) {
+                        const PlaneDev &P = F.pl[c];
+                        float p0 = 0.f, p1 = 0.f;
+                        if (P.use_prob) {
+                            const int cy = s / P.sh;
+                            if (cy < P.ch) {
+                                const float *row = P.gp + (size_t)cy * P.cw;
+                                if (gpx[c][0] >= 0) p0 = fadd(0.f, row[gpx[c][0]]);   // compute.c:62 onto a zeroed gradient
+                                if (gpx[c][1] >= 0) p1 = fadd(0.f, row[gpx[c][1]]);
+                            }
+                        }
+                        const float tvr_l = __shfl_up_sync(0xffffffffu, tvr0[c][1], 1);
+                        float o0 = fadd(fadd(fadd(p0, sv_tvb[c][0]), tvr_l), tvs0[c][0]);          // above, left, self
+                        float o1 = fadd(fadd(fadd(p1, sv_tvb[c][1]), tvr0[c][0]), tvs0[c][1]);
+                        if (use_tgv) {
+                            const float dg_r = __shfl_down_sync(0xffffffffu, sv_dg[c][0], 1);
+                            const float lr_l = __shfl_up_sync(0xffffffffu, lr0[c][1], 1);
+                            const float lr_r = __shfl_down_sync(0xffffffffu, lr0[c][0], 1);
+                            // above, above-right, left, self, right
+                            o0 = fadd(fadd(fadd(fadd(fadd(o0, sv_ud[c][0]), sv_dg[c][1]), lr_l), t2s0[c][0]), lr0[c][1]);
+                            o1 = fadd(fadd(fadd(fadd(fadd(o1, sv_ud[c][1]), dg_r), lr0[c][0]), t2s0[c][1]), lr_r);
+                        }
+                        ogp[c][0] = o0;
+                        ogp[c][1] = o1;
+                    }
+                }
+
+                // ---- rotate ----------------------------------------------------------------------
+#pragma unroll
+                for (int c = 0; c < NC; c++)
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        sv_tvb[c][k] = tvb0[c][k];
+                        sv_ud[c][k] = ud0[c][k];
+                        sv_dg[c][k] = dg0[c][k];
+                        gxP[c][k] = gx0[c][k];
+                        gyP[c][k] = gy0[c][k];
+                    }
+            }
 #pragma unroll
             for (int c = 0; c < NC; c++) {
-                const PlaneDev &P = F.pl[c];
-                float og = 0.f;
-                if (P.use_prob) {
-                    const int cx = px / P.sw, cy = py / P.sh;
-                    if (cx < P.cw && cy < P.ch) og = fadd(0.f, P.gp[(size_t)cy * P.cw + cx]);   // compute.c:62
-                }
-                const int o = c * TS + si;
-                og = fadd(og, tvb[o - G_SW]);          // TV, source above
-                og = fadd(og, tvr[o - 1]);             // TV, source left
-                og = fadd(og, tvs[o]);                 // TV, self
-                if (F.use_tgv) {
-                    og = fadd(og, t2ud[o - G_SW]);     // above
-                    og = fadd(og, t2dg[o - G_SW + 1]); // above-right
-                    og = fadd(og, t2lr[o - 1]);        // left
-                    og = fadd(og, t2s[o]);             // self
-                    og = fadd(og, t2lr[o + 1]);        // right
-                    og = fadd(og, t2dg[o + G_SW - 1]); // below-left
-                    og = fadd(og, t2ud[o + G_SW]);     // below
-                }
-                P.g[gi] = og;
-                acc[c] = __dadd_rn(acc[c], (double)fsq(og));                                    // compute.c:203
+                yP[c][0] = yN[c][0];
+                yP[c][1] = yN[c][1];
             }
         }
     }
 
     // CTA reduction (fixed order => run-to-run deterministic), then the last-CTA fold
-    __shared__ double red[3][G_NT / 32];
+    __shared__ double red[3][GM_WARPS];
     __shared__ unsigned ticket;
-    const int lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x;
 #pragma unroll
     for (int c = 0; c < NC; c++) {
-        const double s = warp_sum(acc[c]);
-        if (lane == 0) red[c][wid] = s;
+        const double sum = warp_sum(acc[c]);
+        if (lane == 0) red[c][wid] = sum;
     }
     __syncthreads();
     const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x, ncta = gridDim.x * gridDim.y;
     if (tid < NC) {
-        double s = 0.;
-        for (int k = 0; k < G_NT / 32; k++) s = __dadd_rn(s, red[tid][k]);
-        F.partials[(size_t)tid * F.grad_ctas + cta] = s;
+        double sum = 0.;
+        for (int k = 0; k < GM_WARPS; k++) sum = __dadd_rn(sum, red[tid][k]);
+        F.partials[(size_t)tid * F.grad_ctas + cta] = sum;
     }
     __threadfence();
     __syncthreads();
@@ -212,16 +311,18 @@ __global__ void __launch_bounds__(G_NT) k_gradient(const __grid_constant__ Frame
         __threadfence();
 #pragma unroll
         for (int c = 0; c < NC; c++) {
-            double s = 0.;
-            for (unsigned k = tid; k < ncta; k += G_NT) s = __dadd_rn(s, __ldcg(&F.partials[(size_t)c * F.grad_ctas + k]));
-            s = warp_sum(s);
-            if (lane == 0) red[c][wid] = s;
+            double sum = 0.;
+            for (unsigned k = tid; k < ncta; k += GM_NT) sum = __dadd_rn(sum, __ldcg(&F.partials[(size_t)c * F.grad_ctas + k]));
+            sum = warp_sum(sum);
+            if (lane == 0) red[c][wid] = sum;
         }
         __syncthreads();
         if (tid < NC) {
-            double s = 0.;
-            for (int k = 0; k < G_NT / 32; k++) s = __dadd_rn(s, red[tid][k]);
-            F.norms[tid] = fsqrt(__double2float_rn(s));                                         // compute.c:205
+            double sum = 0.;
+            for (int k = 0; k < GM_WARPS; k++) sum = __dadd_rn(sum, red[tid][k]);
+            const float norm = fsqrt(__double2float_rn(sum));                                   // compute.c:205
+            F.norms[tid] = norm;
+            F.norms[4 + tid] = __frcp_rn(norm);                                                 // shared reciprocal for k_project
         }
         if (tid == 0) *F.counter = 0u;
     }
@@ -229,70 +330,107 @@ __global__ void __launch_bounds__(G_NT) k_gradient(const __grid_constant__ Frame
 
 // ------------------------------------------------------------------------------------------
 // 8x8 block transposes among the 8 lanes that own one block (lane j holds row j).
-// tile: 8 rows x 9 floats (padded), private to the block.
+// tile: 8 rows x 8 floats; element (r, c) lives at r*8 + (c ^ (((r>>2)&1)<<2)) — the two float4
+// halves of rows 4..7 are swapped, which makes both the 128-bit row accesses and the scalar
+// column accesses bank-conflict free (tiles of the four blocks of a warp are 72 floats apart).
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void transpose8(float (&v)[8], float *tile, int j) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) tile[j * 9 + i] = v[i];
+constexpr int TILE_STRIDE = 72;
+
+__device__ __forceinline__ void rows_to_cols(float (&v)[8], float *tile, int j) {
+    const int h = (j >> 2) & 1;
+    float4 *row = reinterpret_cast<float4 *>(tile + j * 8);
+    row[h] = make_float4(v[0], v[1], v[2], v[3]);
+    row[h ^ 1] = make_float4(v[4], v[5], v[6], v[7]);
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 8; i++) v[i] = tile[i * 9 + j];
+    for (int i = 0; i < 8; i++) v[i] = tile[i * 8 + (j ^ (((i >> 2) & 1) << 2))];
+    __syncwarp();
+}
+__device__ __forceinline__ void cols_to_rows(float (&v)[8], float *tile, int j) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) tile[i * 8 + (j ^ (((i >> 2) & 1) << 2))] = v[i];
+    __syncwarp();
+    const int h = (j >> 2) & 1;
+    const float4 *row = reinterpret_cast<const float4 *>(tile + j * 8);
+    const float4 lo = row[h], hi = row[h ^ 1];
+    v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+    v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
     __syncwarp();
 }
 
 // 2-D transforms for a thread that holds row j of the block and ends holding row j.
 // Vertical pass first, horizontal second (ooura/dct.c:39-94, :103-158).
 __device__ __forceinline__ void fdct8x8_rows(float (&v)[8], float *tile, int j) {
-    transpose8(v, tile, j);
+    rows_to_cols(v, tile, j);
     fdct8(v);
-    transpose8(v, tile, j);
+    cols_to_rows(v, tile, j);
     fdct8(v);
 }
 __device__ __forceinline__ void idct8x8_rows(float (&v)[8], float *tile, int j) {
-    transpose8(v, tile, j);
+    rows_to_cols(v, tile, j);
     idct8(v);
-    transpose8(v, tile, j);
+    cols_to_rows(v, tile, j);
     idct8(v);
 }
 
 // ------------------------------------------------------------------------------------------
-// k_project (v1: 8 threads per coefficient block, 32 blocks per CTA)
+// k_project — 8 threads per coefficient block (thread j owns row j), 32 blocks per CTA.
+// Template <SW, SH>: compile-time sampling factors of the plane (float4 I/O, stepped values of
+// the whole footprint kept in registers); SW == 0 selects the run-time generic path.
 // ------------------------------------------------------------------------------------------
 constexpr int P_NT = 256, P_BW = 8, P_BH = 4;   // CTA tile: 8 x 4 coefficient blocks
 
-struct ProjGrid {
-    int first[4];   // first linear CTA of plane c; first[nc] = total
-    int gx[3];      // CTAs per row of plane c
+struct ProjPlane {
+    int c;          // plane index
+    int gx;         // CTAs per row
 };
 
-__global__ void __launch_bounds__(P_NT) k_project(const __grid_constant__ FrameDev F, const __grid_constant__ ProjGrid G,
-                                                   const float factor) {
-    __shared__ float tiles[P_NT / 8][8 * 9];
+// the stepped point at one frame pixel: y = x + f (x - xp), then y - step * (g / norm)
+// (compute.c:436, :213).  `rn` = RN(1/norm) from k_gradient's last CTA.
+struct Stepper {
+    float factor, step, norm, rn;
+    bool stepping, div_ok;
+    __device__ __forceinline__ float operator()(float x, float xp, float g) const {
+        float y = fadd(x, fmul(factor, fsub(x, xp)));
+        if (stepping) {
+            bool ok = div_ok;
+            float q = qdiv_fast(g, norm, rn, ok);
+            if (!ok) q = fdiv(g, norm);
+            y = fsub(y, fmul(step, q));
+        }
+        return y;
+    }
+};
+
+template <int SW, int SH>
+__global__ void __launch_bounds__(P_NT) k_project(const __grid_constant__ FrameDev F, const ProjPlane G, const float factor) {
+    __shared__ __align__(16) float tiles[2][P_NT / 8][TILE_STRIDE];
+    __shared__ __align__(16) float sq[3][64];          // q, q*q, RN(1/(q*q)) of this plane
     const int tid = threadIdx.x;
-    int c = 0;
-    if ((int)blockIdx.x >= G.first[1]) c = 1;
-    if ((int)blockIdx.x >= G.first[2]) c = 2;
-    const int rel = blockIdx.x - G.first[c];
-    const int ctay = rel / G.gx[c], ctax = rel - ctay * G.gx[c];
+    const int c = G.c;
     const PlaneDev &P = F.pl[c];
+    if (tid < 64) {
+        sq[0][tid] = F.q[c][tid];
+        sq[1][tid] = F.qq[c][tid];
+        sq[2][tid] = F.rqq[c][tid];
+    }
+    __syncthreads();
+    const int ctay = blockIdx.x / G.gx, ctax = blockIdx.x - ctay * G.gx;
     const int W = F.W, H = F.H;
     const int b = tid >> 3, j = tid & 7;
     const int bx = ctax * P_BW + (b & (P_BW - 1)), by = ctay * P_BH + (b >> 3);
     const bool real = bx < (P.cw >> 3) && by < (P.ch >> 3);
-    const float norm = F.norms[c];
-    const float step = F.step;
-    const int sw = P.sw, sh = P.sh;
-    float *tile = tiles[b];
-
-    // the stepped point at one frame pixel (compute.c:436 then :213)
-    auto stepped = [&](size_t gi) -> float {
-        const float a = P.x[gi], p = P.xp[gi];
-        float y = fadd(a, fmul(factor, fsub(a, p)));
-        if (norm != 0.f) y = fsub(y, fmul(step, fdiv(P.g[gi], norm)));
-        return y;
-    };
-
+    const int sw = SW ? SW : P.sw, sh = SW ? SH : P.sh;
+    Stepper stepper;
+    stepper.factor = factor;
+    stepper.step = F.step;
+    stepper.norm = F.norms[c];
+    stepper.rn = F.norms[4 + c];
+    stepper.stepping = stepper.norm != 0.f;                        // compute.c:211
+    stepper.div_ok = qdiv_divisor_ok(stepper.norm);
+    float *tileA = tiles[0][b], *tileB = tiles[1][b];
     const int cy = by * 8 + j;
+
     if (!real) {
         // pixels of the frame that no coefficient block covers: step only (compute.c:349-350 never visits them)
         for (int i = 0; i < 8; i++)
@@ -301,69 +439,153 @@ __global__ void __launch_bounds__(P_NT) k_project(const __grid_constant__ FrameD
                     const int px = (bx * 8 + i) * sw + sx, py = cy * sh + sy;
                     if (px < W && py < H) {
                         const size_t gi = (size_t)py * W + px;
-                        P.xp[gi] = stepped(gi);
+                        P.xp[gi] = stepper(P.x[gi], P.xp[gi], P.g[gi]);
                     }
                 }
         return;   // whole 8-lane groups leave together; the remaining lanes still __syncwarp among themselves
     }
 
+    // ---- stepped point of the footprint, block-row means (compute.c:348-370) ------------------
+    constexpr int ZW = SW ? SW * 8 : 1, ZH = SW ? SH : 1;
+    float z[ZH][ZW];
     float v[8], mean[8];
+    if constexpr (SW > 0) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const int cx = bx * 8 + i;
-        if (P.resample) {
-            float m = 0.f;                                                   // compute.c:351
-            for (int sy = 0; sy < sh; sy++)
-                for (int sx = 0; sx < sw; sx++) m = fadd(m, stepped((size_t)(cy * sh + sy) * W + cx * sw + sx));
-            m = fdiv(m, P.cnt);                                      // compute.c:359
-            mean[i] = m;
-            v[i] = m;
-        } else {
-            mean[i] = 0.f;
-            v[i] = stepped((size_t)cy * W + cx);
+        for (int sy = 0; sy < SH; sy++) {
+            const size_t gi = (size_t)(cy * SH + sy) * W + (size_t)bx * 8 * SW;
+            const float4 *xr = reinterpret_cast<const float4 *>(P.x + gi);
+            const float4 *pr = reinterpret_cast<const float4 *>(P.xp + gi);
+            const float4 *gr = reinterpret_cast<const float4 *>(P.g + gi);
+#pragma unroll
+            for (int k = 0; k < SW * 2; k++) {
+                const float4 a = xr[k], p = pr[k], g = gr[k];
+                z[sy][k * 4 + 0] = stepper(a.x, p.x, g.x);
+                z[sy][k * 4 + 1] = stepper(a.y, p.y, g.y);
+                z[sy][k * 4 + 2] = stepper(a.z, p.z, g.z);
+                z[sy][k * 4 + 3] = stepper(a.w, p.w, g.w);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (SW * SH > 1 || P.resample) {
+                float m = 0.f;                                               // compute.c:351
+#pragma unroll
+                for (int sy = 0; sy < SH; sy++)
+#pragma unroll
+                    for (int sx = 0; sx < SW; sx++) m = fadd(m, z[sy][i * SW + sx]);
+                constexpr int CNT = SW * SH;
+                if constexpr ((CNT & (CNT - 1)) == 0) m = fmul(m, 1.0f / CNT);   // exact: power-of-two divisor
+                else m = fdiv(m, (float)CNT);                                // compute.c:359
+                mean[i] = m;
+                v[i] = m;
+            } else {
+                mean[i] = 0.f;
+                v[i] = z[0][i];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int cx = bx * 8 + i;
+            if (P.resample) {
+                float m = 0.f;
+                for (int sy = 0; sy < sh; sy++)
+                    for (int sx = 0; sx < sw; sx++) {
+                        const size_t gi = (size_t)(cy * sh + sy) * W + cx * sw + sx;
+                        m = fadd(m, stepper(P.x[gi], P.xp[gi], P.g[gi]));
+                    }
+                m = fdiv(m, P.cnt);
+                mean[i] = m;
+                v[i] = m;
+            } else {
+                const size_t gi = (size_t)cy * W + cx;
+                mean[i] = 0.f;
+                v[i] = stepper(P.x[gi], P.xp[gi], P.g[gi]);
+            }
         }
     }
 
-    fdct8x8_rows(v, tile, j);
+    fdct8x8_rows(v, tileA, j);
 
-    // clamp to the quantisation interval (compute.c:323-331) and form the DCT-distance residual
+    // ---- clamp to the quantisation interval (compute.c:323-331); DCT-distance residual ---------
     const int16_t *drow = P.data + ((size_t)(by * (P.cw >> 3) + bx) * 64 + j * 8);
     const int4 draw = *reinterpret_cast<const int4 *>(drow);
     const int dw[4] = {draw.x, draw.y, draw.z, draw.w};
+    float qv[8], qqv[8], rqv[8];
+    {
+        const float4 *t0 = reinterpret_cast<const float4 *>(&sq[0][j * 8]);
+        const float4 *t1 = reinterpret_cast<const float4 *>(&sq[1][j * 8]);
+        const float4 *t2 = reinterpret_cast<const float4 *>(&sq[2][j * 8]);
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const float4 a = t0[k], bq = t1[k], cq = t2[k];
+            qv[k * 4] = a.x; qv[k * 4 + 1] = a.y; qv[k * 4 + 2] = a.z; qv[k * 4 + 3] = a.w;
+            qqv[k * 4] = bq.x; qqv[k * 4 + 1] = bq.y; qqv[k * 4 + 2] = bq.z; qqv[k * 4 + 3] = bq.w;
+            rqv[k * 4] = cq.x; rqv[k * 4 + 1] = cq.y; rqv[k * 4 + 2] = cq.z; rqv[k * 4 + 3] = cq.w;
+        }
+    }
     float r[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         const int di = (i & 1) ? (dw[i >> 1] >> 16) : (int)(short)(dw[i >> 1] & 0xffff);
         const float d = (float)di;
-        const float q = F.q[c][j * 8 + i];
+        const float q = qv[i];
         const float lo = fmul(fsub(d, 0.5f), q), hi = fmul(fadd(d, 0.5f), q);
         float t = v[i];
         t = t > hi ? hi : (t < lo ? lo : t);
         v[i] = t;
-        r[i] = fdiv(fsub(t, fmul(d, q)), F.qq[c][j * 8 + i]);                // compute.c:47,49
+        const float num = fsub(t, fmul(d, q));                               // compute.c:47
+        bool ok = true;                                                      // q*q in [1, 2^32]: always a valid divisor
+        float rr = qdiv_fast(num, qqv[i], rqv[i], ok);
+        if (!ok) rr = fdiv(num, qqv[i]);                                     // compute.c:49
+        r[i] = rr;
     }
 
-    idct8x8_rows(v, tile, j);
+    idct8x8_rows(v, tileA, j);
     if (P.use_prob) {
-        idct8x8_rows(r, tile, j);
-        float *gprow = P.gp + (size_t)cy * P.cw + bx * 8;
-#pragma unroll
-        for (int i = 0; i < 8; i++) gprow[i] = fmul(P.p_alpha, r[i]);         // compute.c:62 (the product)
+        idct8x8_rows(r, tileB, j);
+        float4 *gprow = reinterpret_cast<float4 *>(P.gp + (size_t)cy * P.cw + bx * 8);
+        const float pa = P.p_alpha;                                          // compute.c:62 (the product)
+        gprow[0] = make_float4(fmul(pa, r[0]), fmul(pa, r[1]), fmul(pa, r[2]), fmul(pa, r[3]));
+        gprow[1] = make_float4(fmul(pa, r[4]), fmul(pa, r[5]), fmul(pa, r[6]), fmul(pa, r[7]));
     }
 
-    // write x_{k+1} (compute.c:387-403)
+    // ---- write x_{k+1} (compute.c:387-403) -------------------------------------------------------
+    if constexpr (SW > 0) {
+        if (SW * SH > 1 || P.resample) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const int cx = bx * 8 + i;
-        if (P.resample) {
-            for (int sy = 0; sy < sh; sy++)
-                for (int sx = 0; sx < sw; sx++) {
-                    const size_t gi = (size_t)(cy * sh + sy) * W + cx * sw + sx;
-                    const float z = stepped(gi);
-                    P.xp[gi] = fadd(fsub(z, mean[i]), v[i]);
+            for (int sy = 0; sy < SH; sy++) {
+                float4 *o = reinterpret_cast<float4 *>(P.xp + (size_t)(cy * SH + sy) * W + (size_t)bx * 8 * SW);
+#pragma unroll
+                for (int k = 0; k < SW * 2; k++) {
+                    float e[4];
+#pragma unroll
+                    for (int m = 0; m < 4; m++) {
+                        const int col = k * 4 + m, i = col / SW;
+                        e[m] = fadd(fsub(z[sy][col], mean[i]), v[i]);
+                    }
+                    o[k] = make_float4(e[0], e[1], e[2], e[3]);
                 }
+            }
         } else {
-            P.xp[(size_t)cy * W + cx] = v[i];
+            float4 *o = reinterpret_cast<float4 *>(P.xp + (size_t)cy * W + (size_t)bx * 8);
+            o[0] = make_float4(v[0], v[1], v[2], v[3]);
+            o[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int cx = bx * 8 + i;
+            if (P.resample) {
+                for (int sy = 0; sy < sh; sy++)
+                    for (int sx = 0; sx < sw; sx++) {
+                        const size_t gi = (size_t)(cy * sh + sy) * W + cx * sw + sx;
+                        const float zz = stepper(P.x[gi], P.xp[gi], P.g[gi]);
+                        P.xp[gi] = fadd(fsub(zz, mean[i]), v[i]);
+                    }
+            } else {
+                P.xp[(size_t)cy * W + cx] = v[i];
+            }
         }
     }
 }
@@ -373,7 +595,7 @@ __global__ void __launch_bounds__(P_NT) k_project(const __grid_constant__ FrameD
 // ------------------------------------------------------------------------------------------
 // conventional decode of one plane: dequantise + IDCT + raster (jpeg.c:83-92, jpeg2png.c:131-139)
 __global__ void __launch_bounds__(P_NT) k_decode(const int16_t *data, const float *q /*[64] device*/, float *out, int cw, int ch) {
-    __shared__ float tiles[P_NT / 8][8 * 9];
+    __shared__ __align__(16) float tiles[P_NT / 8][TILE_STRIDE];
     const int tid = threadIdx.x, b = tid >> 3, j = tid & 7;
     const int nb = (cw >> 3) * (ch >> 3);
     const int blk = blockIdx.x * (P_NT / 8) + b;
@@ -407,46 +629,69 @@ __global__ void k_init_plane(const float *fdata, float *x, float *xp, int W, int
 // ------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------
-static size_t grad_smem(int nc) { return (size_t)(nc * G_YH * G_YW + 7 * nc * G_SH * G_SW) * sizeof(float); }
+// Band height: one resident wave of CTAs if the frame allows it (long bands amortise the two
+// extra source rows each band recomputes), never fewer than 8 rows per band.
+static int g_grad_slots = 0;   // CTAs resident on the whole device, set by configure_kernels()
 
-int grad_cta_count(int W, int H) { return ((W + G_TW - 1) / G_TW) * ((H + G_TH - 1) / G_TH); }
+void grad_geometry(int W, int H, int *ctas_x, int *bands, int *band_rows) {
+    const int strips = (W + GM_USE - 1) / GM_USE;
+    *ctas_x = (strips + GM_WARPS - 1) / GM_WARPS;
+    const int slots = g_grad_slots > 0 ? g_grad_slots : 148 * 3;
+    int want = slots / *ctas_x;
+    if (want < 1) want = 1;
+    int rows = (H + want - 1) / want;
+    if (rows < 8) rows = 8;
+    *band_rows = rows;
+    *bands = (H + rows - 1) / rows;
+}
+
+int grad_cta_count(int W, int H) {
+    int cx, b, r;
+    grad_geometry(W, H, &cx, &b, &r);
+    return cx * b;
+}
 
 cudaError_t configure_kernels() {
-    cudaError_t e;
-    e = cudaFuncSetAttribute(k_gradient<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grad_smem(1));
+    int per_sm = 0, dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_gradient<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grad_smem(2));
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_gradient<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grad_smem(3));
-    return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gradient<3>, GM_NT, 0);
+    if (e != cudaSuccess) return e;
+    g_grad_slots = sms * (per_sm > 0 ? per_sm : 1);
+    return cudaSuccess;
 }
 
 cudaError_t launch_gradient(const FrameDev &F, float factor, cudaStream_t s) {
-    dim3 grid((F.W + G_TW - 1) / G_TW, (F.H + G_TH - 1) / G_TH);
+    int cx, bands, rows;
+    grad_geometry(F.W, F.H, &cx, &bands, &rows);
+    dim3 grid(cx, bands);
     switch (F.nc) {
-        case 1: k_gradient<1><<<grid, G_NT, grad_smem(1), s>>>(F, factor); break;
-        case 2: k_gradient<2><<<grid, G_NT, grad_smem(2), s>>>(F, factor); break;
-        default: k_gradient<3><<<grid, G_NT, grad_smem(3), s>>>(F, factor); break;
+        case 1: k_gradient<1><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
+        case 2: k_gradient<2><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
+        default: k_gradient<3><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
     }
     return cudaGetLastError();
 }
 
 cudaError_t launch_project(const FrameDev &F, float factor, cudaStream_t s) {
-    ProjGrid G;
-    int total = 0;
-    for (int c = 0; c < 3; c++) {
-        G.first[c] = total;
-        G.gx[c] = 1;
-        if (c < F.nc) {
-            const int tw = 8 * P_BW * F.pl[c].sw, th = 8 * P_BH * F.pl[c].sh;
-            G.gx[c] = (F.W + tw - 1) / tw;
-            total += G.gx[c] * ((F.H + th - 1) / th);
-        }
+    for (int c = 0; c < F.nc; c++) {
+        const PlaneDev &P = F.pl[c];
+        const int tw = 8 * P_BW * P.sw, th = 8 * P_BH * P.sh;
+        ProjPlane G;
+        G.c = c;
+        G.gx = (F.W + tw - 1) / tw;
+        const int total = G.gx * ((F.H + th - 1) / th);
+        if (P.sw == 1 && P.sh == 1) k_project<1, 1><<<total, P_NT, 0, s>>>(F, G, factor);
+        else if (P.sw == 2 && P.sh == 2) k_project<2, 2><<<total, P_NT, 0, s>>>(F, G, factor);
+        else if (P.sw == 2 && P.sh == 1) k_project<2, 1><<<total, P_NT, 0, s>>>(F, G, factor);
+        else if (P.sw == 1 && P.sh == 2) k_project<1, 2><<<total, P_NT, 0, s>>>(F, G, factor);
+        else k_project<0, 0><<<total, P_NT, 0, s>>>(F, G, factor);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
     }
-    G.first[3] = total;
-    for (int c = F.nc; c < 3; c++) G.first[c] = total;
-    k_project<<<total, P_NT, 0, s>>>(F, G, factor);
-    return cudaGetLastError();
+    return cudaSuccess;
 }
 
 cudaError_t launch_decode(const int16_t *data, const float *q_dev, float *out, int cw, int ch, cudaStream_t s) {

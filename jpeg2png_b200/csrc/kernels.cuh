@@ -25,12 +25,13 @@ struct FrameDev {
     PlaneDev pl[3];
     float q[3][64];       // quantisation tables as float
     float qq[3][64];      // q*q (fp32 product, compute.c:49)
+    float rqq[3][64];     // RN(1/(q*q)), the shared reciprocal of the residual division
     float a1;             // (float)(1./sqrtf(nc))                          (compute.c:90)
     float a2;             // (float)(alpha*1./sqrtf(nc)), alpha = weight/sqrtf(2)   (compute.c:154,258)
     int use_tgv;          // weight != 0                                    (compute.c:257)
     float step;           // radius / sqrtf(1 + iterations)                 (compute.c:425,443)
     double *partials;     // [3][grad_ctas] per-CTA sums of g^2
-    float *norms;         // [3] sqrtf((float)sum g^2)                      (compute.c:200-206)
+    float *norms;         // [0..2] sqrtf((float)sum g^2) (compute.c:200-206); [4..6] RN(1/norm)
     unsigned *counter;    // CTAs-done ticket for the last-CTA reduction
     double *log_acc;      // [4][grad_ctas] optional objective partials (tv, tv2) + [3][proj] prob
     int grad_ctas;

@@ -175,10 +175,10 @@ static int create_impl(j2p_session *s, int device, const j2p_frame_desc *d) {
     }
     F.grad_ctas = grad_cta_count(F.W, F.H);
     CK(cudaMalloc(&F.partials, sizeof(double) * 3 * (size_t)F.grad_ctas));
-    CK(cudaMalloc(&F.norms, sizeof(float) * 4));
+    CK(cudaMalloc(&F.norms, sizeof(float) * 8));
     CK(cudaMalloc(&F.counter, sizeof(unsigned)));
     CK(cudaMemsetAsync(F.counter, 0, sizeof(unsigned), s->stream));
-    CK(cudaMemsetAsync(F.norms, 0, sizeof(float) * 4, s->stream));
+    CK(cudaMemsetAsync(F.norms, 0, sizeof(float) * 8, s->stream));
     return J2P_OK;
 }
 
@@ -236,6 +236,7 @@ extern "C" int j2p_session_upload(j2p_session *s, unsigned c, const int16_t *dat
         qf[j] = (float)quant[j];
         F.q[c][j] = qf[j];
         F.qq[c][j] = qf[j] * qf[j];                                     // fp32 product (compute.c:49)
+        F.rqq[c][j] = (float)(1.0 / (double)F.qq[c][j]);                // RN(1/qq): fp64 quotient narrowed once is correctly rounded
     }
     CK(cudaMemcpyAsync(s->qdev[c], qf, sizeof qf, cudaMemcpyHostToDevice, s->stream));
     CK(cudaMemcpyAsync(s->data[c], data, nc * sizeof(int16_t), cudaMemcpyHostToDevice, s->stream));
@@ -266,7 +267,7 @@ static int one_iteration(j2p_session *s, cudaEvent_t e0, cudaEvent_t e1, cudaEve
     if (e1) CK(cudaEventRecord(e1, s->stream));
     CK(launch_project(F, factor, s->stream));
     if (e2) CK(cudaEventRecord(e2, s->stream));
-    s->launches += 2;
+    s->launches += 1 + (unsigned)F.nc;
     for (int c = 0; c < F.nc; c++) {                                    // compute.c:438
         float *tmp = F.pl[c].x;
         F.pl[c].x = F.pl[c].xp;
