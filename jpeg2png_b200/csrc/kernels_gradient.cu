@@ -1,0 +1,406 @@
+// kernels_gradient.cu — sm_100a sub-gradient kernel of the jpeg2png solver.
+//
+// One solver iteration (reference compute.c:427-453) is two kernels:
+//
+//   k_gradient  (this file): FISTA extrapolation y = x_k + f (x_k - x_{k-1}) recomputed on the
+//                 fly (compute.c:431-440), TV sub-gradient (compute.c:73-113), second-order TGV
+//                 sub-gradient (compute.c:128-186) restated as an ordered per-pixel GATHER
+//                 (SURVEY.md §8a), plus the DCT-distance term read from `gp`; writes g and the
+//                 per-CTA fp64 partial sums of g^2; the last CTA to finish folds the partials
+//                 into the three norms of compute.c:200-206 (and their reciprocals).
+//   k_project   (kernels_project.cu): step, projection, next DCT-distance gradient.
+//
+// box()/unbox() (box.c) are addressing only.  No tensor cores: the path is a stencil plus
+// block-local 8-point butterflies in emulated-reference arithmetic (numerics.cuh).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.cuh"
+#include "numerics.cuh"
+
+namespace j2p {
+
+// ------------------------------------------------------------------------------------------
+// k_gradient — register-marching, warp-autonomous stencil.
+//
+// A warp owns a vertical strip of 64 frame columns (60 target columns + a 2-column halo on each
+// side), two adjacent columns per lane, and walks down a band of rows.  All three stages of the
+// sub-gradient live in registers; horizontal neighbours are exchanged with warp shuffles (eight
+// per channel and row), vertical neighbours are the values the lane itself produced one and two
+// rows earlier.  No shared memory, no block barrier in the main loop.  The loads of row i+1 (and
+// of the DCT-distance term of the next target row) are issued one full row-step before use.
+//
+// Row pipeline at step i (the FISTA point of row i has just been formed):
+//   source row s = i-1 : forward differences, joint TV norm and the three TV quotients
+//                        (compute.c:73-113); backward differences of the differences, joint TGV
+//                        norm and the four TGV quotients (compute.c:128-186)
+//   target row s-1     : receives its last two addends (below-left, below) and is stored
+//   target row s       : receives its first nine addends, in the one order that reproduces the
+//                        reference's scan-order scatter
+//
+// Frame borders: the reference forces a difference to 0 where the neighbour does not exist
+// (compute.c:79-81, :137-143).  Here the missing neighbour is replaced by the pixel itself, so
+// the same subtraction yields the same +0 (all values are finite).  Sources outside the frame,
+// and sources whose norm is 0 (compute.c:97, :158), contribute nothing: their shared reciprocal
+// is set to 0, which makes every quotient of that pixel exactly 0.
+// ------------------------------------------------------------------------------------------
+constexpr int GM_WARPS = 4, GM_NT = GM_WARPS * 32, GM_USE = 60;
+
+template <int NC>
+__global__ void __launch_bounds__(GM_NT) k_gradient(const __grid_constant__ FrameDev F, const float factor, const int band_rows) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int W = F.W, H = F.H;
+    const int X0 = (blockIdx.x * GM_WARPS + wid) * GM_USE;   // first target column of this warp
+    const int yb = blockIdx.y * band_rows;                   // first target row of this CTA
+    const int ye = min(yb + band_rows, H);
+    const int px0 = X0 - 2 + 2 * lane;                       // even; W is even => the pair is in or out together
+    const bool pair_in = px0 >= 0 && px0 < W;
+    const bool is_target = pair_in && lane >= 1 && lane <= 30;
+    const bool has_l0 = px0 > 0, has_r1 = px0 + 1 < W - 1;   // k=1 always has a left neighbour, k=0 a right one
+    const float a1 = F.a1, a2 = F.a2;
+    const bool use_tgv = F.use_tgv != 0;
+
+    double acc[NC];
+    float yP[NC][2], gxP[NC][2], gyP[NC][2], ogp[NC][2], sv_tvb[NC][2], sv_ud[NC][2], sv_dg[NC][2];
+    float2 ldx[NC], ldp[NC];      // x_k / x_{k-1} of the row after the one being formed
+    float pgp[NC][2];             // DCT-distance term of the next target row
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        acc[c] = 0.;
+        ldx[c] = ldp[c] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 2; k++) yP[c][k] = gxP[c][k] = gyP[c][k] = ogp[c][k] = sv_tvb[c][k] = sv_ud[c][k] = sv_dg[c][k] = pgp[c][k] = 0.f;
+    }
+    // coefficient-grid column of each of the two pixels (the DCT-distance term is stored at
+    // coefficient resolution); -1 = this pixel has no such term (compute.c:58-62 footprint)
+    int gpx[NC][2];
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int cx = (px0 + k) / F.pl[c].sw;
+            gpx[c][k] = (F.pl[c].use_prob && pair_in && cx < F.pl[c].cw) ? cx : -1;
+        }
+
+    auto issue_row_loads = [&](int row) {
+        const bool ld = pair_in && row >= 0 && row < H;
+        if (ld) {
+            const size_t gi = (size_t)row * W + px0;
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                ldx[c] = *reinterpret_cast<const float2 *>(F.pl[c].x + gi);
+                ldp[c] = *reinterpret_cast<const float2 *>(F.pl[c].xp + gi);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < NC; c++) ldx[c] = ldp[c] = make_float2(0.f, 0.f);
+        }
+    };
+    auto issue_gp_loads = [&](int row) {
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            const PlaneDev &P = F.pl[c];
+            pgp[c][0] = pgp[c][1] = 0.f;
+            if (P.use_prob && row >= 0) {
+                const int cy = row / P.sh;
+                if (cy < P.ch) {
+                    const float *gr = P.gp + (size_t)cy * P.cw;
+                    if (gpx[c][0] >= 0) pgp[c][0] = gr[gpx[c][0]];
+                    if (gpx[c][1] >= 0) pgp[c][1] = gr[gpx[c][1]];
+                }
+            }
+        }
+    };
+
+    if (X0 < W) {
+        issue_row_loads(yb - 2);
+        for (int i = yb - 2; i <= ye + 1; i++) {
+            // ---- FISTA point of row i (compute.c:436) from the loads issued one step ago -------
+            float yN[NC][2];
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                yN[c][0] = fadd(ldx[c].x, fmul(factor, fsub(ldx[c].x, ldp[c].x)));
+                yN[c][1] = fadd(ldx[c].y, fmul(factor, fsub(ldx[c].y, ldp[c].y)));
+            }
+            float gpv[NC][2];
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                gpv[c][0] = pgp[c][0];
+                gpv[c][1] = pgp[c][1];
+            }
+            if (i < ye + 1) issue_row_loads(i + 1);
+            if (i >= yb && i < ye) issue_gp_loads(i);              // consumed next step, where the target row is s = i
+
+            if (i >= yb - 1) {
+                const int s = i - 1;
+                const bool src_in = pair_in && s >= 0 && s < H;
+                if (s >= H - 1) {                                   // no row below: gy := 0 (compute.c:81)
+#pragma unroll
+                    for (int c = 0; c < NC; c++) { yN[c][0] = yP[c][0]; yN[c][1] = yP[c][1]; }
+                }
+
+                // ---- source row s: TV (compute.c:79-105) ---------------------------------------
+                float gx0[NC][2], gy0[NC][2], tvs0[NC][2], tvr0[NC][2], tvb0[NC][2];
+                float n1[2] = {0.f, 0.f};
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    float yr1 = __shfl_down_sync(0xffffffffu, yP[c][0], 1);
+                    yr1 = has_r1 ? yr1 : yP[c][1];                  // no right neighbour: gx := 0 (compute.c:79)
+                    gx0[c][0] = fsub(yP[c][1], yP[c][0]);
+                    gx0[c][1] = fsub(yr1, yP[c][1]);
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        gy0[c][k] = fsub(yN[c][k], yP[c][k]);
+                        n1[k] = fadd(n1[k], fsq(gx0[c][k]));
+                        n1[k] = fadd(n1[k], fsq(gy0[c][k]));
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    const float n = fsqrt(n1[k]);
+                    const bool live = src_in && n != 0.f;                         // compute.c:97
+                    const float y = live ? __frcp_rn(n) : 0.f;
+                    unsigned key = 0xffffffffu;
+                    float num[NC][3];
+#pragma unroll
+                    for (int c = 0; c < NC; c++) {
+                        num[c][0] = fmul(a1, -fadd(gx0[c][k], gy0[c][k]));                         // compute.c:98
+                        num[c][1] = fmul(a1, gx0[c][k]);                                           // compute.c:100
+                        num[c][2] = fmul(a1, gy0[c][k]);                                           // compute.c:103
+                        key = min(key, min(qdiv_key(num[c][0]), min(qdiv_key(num[c][1]), qdiv_key(num[c][2]))));
+                        tvs0[c][k] = qdiv_core(num[c][0], n, y);
+                        tvr0[c][k] = qdiv_core(num[c][1], n, y);
+                        tvb0[c][k] = qdiv_core(num[c][2], n, y);
+                    }
+                    if (live && !(key >= QDIV_KEY_MIN && qdiv_divisor_ok(n))) {    // outside the proven range: IEEE division
+#pragma unroll
+                        for (int c = 0; c < NC; c++) {
+                            tvs0[c][k] = fdiv(num[c][0], n);
+                            tvr0[c][k] = fdiv(num[c][1], n);
+                            tvb0[c][k] = fdiv(num[c][2], n);
+                        }
+                    }
+                }
+
+                // ---- source row s: second-order TGV (compute.c:136-183) ------------------------
+                float t2s0[NC][2], lr0[NC][2], ud0[NC][2], dg0[NC][2];
+                if (use_tgv && i >= yb) {
+                    if (s <= 0) {                                   // no row above: gxy, gyy := 0 (compute.c:141-143)
+#pragma unroll
+                        for (int c = 0; c < NC; c++)
+#pragma unroll
+                            for (int k = 0; k < 2; k++) { gxP[c][k] = gx0[c][k]; gyP[c][k] = gy0[c][k]; }
+                    }
+                    float gxx[NC][2], gyy[NC][2], sym[NC][2];
+                    float n2[2] = {0.f, 0.f};
+#pragma unroll
+                    for (int c = 0; c < NC; c++) {
+                        float gxl = __shfl_up_sync(0xffffffffu, gx0[c][1], 1);
+                        float gyl = __shfl_up_sync(0xffffffffu, gy0[c][1], 1);
+                        gxl = has_l0 ? gxl : gx0[c][0];             // no left neighbour: gxx, gyx := 0 (compute.c:137-139)
+                        gyl = has_l0 ? gyl : gy0[c][0];
+#pragma unroll
+                        for (int k = 0; k < 2; k++) {
+                            const float gx_l = k ? gx0[c][0] : gxl, gy_l = k ? gy0[c][0] : gyl;
+                            gxx[c][k] = fsub(gx0[c][k], gx_l);
+                            const float gyx = fsub(gy0[c][k], gy_l);
+                            const float gxy = fsub(gx0[c][k], gxP[c][k]);
+                            gyy[c][k] = fsub(gy0[c][k], gyP[c][k]);
+                            sym[c][k] = fmul(fadd(gxy, gyx), 0.5f);               // (gxy+gyx)/2., exact either way
+                            n2[k] = fadd(n2[k], fadd(fadd(fsq(gxx[c][k]), fmul(2.f, fsq(sym[c][k]))), fsq(gyy[c][k])));
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        const float n = fsqrt(n2[k]);
+                        const bool live = src_in && n != 0.f;                     // compute.c:158
+                        const float y = live ? __frcp_rn(n) : 0.f;
+                        unsigned key = 0xffffffffu;
+                        float num[NC][4];
+#pragma unroll
+                        for (int c = 0; c < NC; c++) {
+                            num[c][0] = -fadd(fadd(fmul(2.f, gxx[c][k]), fmul(2.f, sym[c][k])), fmul(2.f, gyy[c][k]));
+                            num[c][1] = fadd(sym[c][k], gxx[c][k]);
+                            num[c][2] = fadd(gyy[c][k], sym[c][k]);
+                            num[c][3] = -sym[c][k];
+                            key = min(min(key, qdiv_key(num[c][0])), min(qdiv_key(num[c][1]), min(qdiv_key(num[c][2]), qdiv_key(num[c][3]))));
+                            t2s0[c][k] = qdiv_core(num[c][0], n, y);
+                            lr0[c][k] = qdiv_core(num[c][1], n, y);
+                            ud0[c][k] = qdiv_core(num[c][2], n, y);
+                            dg0[c][k] = qdiv_core(num[c][3], n, y);
+                        }
+                        if (live && !(key >= QDIV_KEY_MIN && qdiv_divisor_ok(n))) {
+#pragma unroll
+                            for (int c = 0; c < NC; c++) {
+                                t2s0[c][k] = fdiv(num[c][0], n);
+                                lr0[c][k] = fdiv(num[c][1], n);
+                                ud0[c][k] = fdiv(num[c][2], n);
+                                dg0[c][k] = fdiv(num[c][3], n);
+                            }
+                        }
+#pragma unroll
+                        for (int c = 0; c < NC; c++) {
+                            t2s0[c][k] = fmul(a2, t2s0[c][k]);                    // compute.c:165
+                            lr0[c][k] = fmul(a2, lr0[c][k]);                      // compute.c:167,170
+                            ud0[c][k] = fmul(a2, ud0[c][k]);                      // compute.c:173,176
+                            dg0[c][k] = fmul(a2, dg0[c][k]);                      // compute.c:179,182
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < NC; c++)
+#pragma unroll
+                        for (int k = 0; k < 2; k++) t2s0[c][k] = lr0[c][k] = ud0[c][k] = dg0[c][k] = 0.f;
+                }
+
+                // ---- target row s-1: last two addends, store, sum of squares -------------------
+                if (i >= yb + 2) {
+                    const size_t gi = (size_t)(s - 1) * W + (is_target ? px0 : 0);
+#pragma unroll
+                    for (int c = 0; c < NC; c++) {
+                        float o0 = ogp[c][0], o1 = ogp[c][1];
+                        if (use_tgv) {
+                            const float dgl = __shfl_up_sync(0xffffffffu, dg0[c][1], 1);
+                            o0 = fadd(fadd(o0, dgl), ud0[c][0]);                  // below-left, below
+                            o1 = fadd(fadd(o1, dg0[c][0]), ud0[c][1]);
+                        }
+                        if (is_target) {
+                            *reinterpret_cast<float2 *>(F.pl[c].g + gi) = make_float2(o0, o1);
+                            acc[c] = __dadd_rn(acc[c], (double)fsq(o0));          // compute.c:203
+                            acc[c] = __dadd_rn(acc[c], (double)fsq(o1));
+                        }
+                    }
+                }
+
+                // ---- target row s: first nine addends ------------------------------------------
+                if (s >= yb && s < ye) {
+#pragma unroll
+                    for (int c = 0; c < NC; c++) {
+                        const float p0 = fadd(0.f, gpv[c][0]), p1 = fadd(0.f, gpv[c][1]);           // compute.c:62 onto a zeroed gradient
+                        const float tvr_l = __shfl_up_sync(0xffffffffu, tvr0[c][1], 1);
+                        float o0 = fadd(fadd(fadd(p0, sv_tvb[c][0]), tvr_l), tvs0[c][0]);          // above, left, self
+                        float o1 = fadd(fadd(fadd(p1, sv_tvb[c][1]), tvr0[c][0]), tvs0[c][1]);
+                        if (use_tgv) {
+                            const float dg_r = __shfl_down_sync(0xffffffffu, sv_dg[c][0], 1);
+                            const float lr_l = __shfl_up_sync(0xffffffffu, lr0[c][1], 1);
+                            const float lr_r = __shfl_down_sync(0xffffffffu, lr0[c][0], 1);
+                            // above, above-right, left, self, right
+                            o0 = fadd(fadd(fadd(fadd(fadd(o0, sv_ud[c][0]), sv_dg[c][1]), lr_l), t2s0[c][0]), lr0[c][1]);
+                            o1 = fadd(fadd(fadd(fadd(fadd(o1, sv_ud[c][1]), dg_r), lr0[c][0]), t2s0[c][1]), lr_r);
+                        }
+                        ogp[c][0] = o0;
+                        ogp[c][1] = o1;
+                    }
+                }
+
+                // ---- rotate ----------------------------------------------------------------------
+#pragma unroll
+                for (int c = 0; c < NC; c++)
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        sv_tvb[c][k] = tvb0[c][k];
+                        sv_ud[c][k] = ud0[c][k];
+                        sv_dg[c][k] = dg0[c][k];
+                        gxP[c][k] = gx0[c][k];
+                        gyP[c][k] = gy0[c][k];
+                    }
+            }
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                yP[c][0] = yN[c][0];
+                yP[c][1] = yN[c][1];
+            }
+        }
+    }
+
+    // CTA reduction (fixed order => run-to-run deterministic), then the last-CTA fold
+    __shared__ double red[3][GM_WARPS];
+    __shared__ unsigned ticket;
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        const double sum = warp_sum(acc[c]);
+        if (lane == 0) red[c][wid] = sum;
+    }
+    __syncthreads();
+    const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x, ncta = gridDim.x * gridDim.y;
+    if (tid < NC) {
+        double sum = 0.;
+        for (int k = 0; k < GM_WARPS; k++) sum = __dadd_rn(sum, red[tid][k]);
+        F.partials[(size_t)tid * F.grad_ctas + cta] = sum;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) ticket = atomicAdd(F.counter, 1u);
+    __syncthreads();
+    if (ticket == ncta - 1) {
+        __threadfence();
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            double sum = 0.;
+            for (unsigned k = tid; k < ncta; k += GM_NT) sum = __dadd_rn(sum, __ldcg(&F.partials[(size_t)c * F.grad_ctas + k]));
+            sum = warp_sum(sum);
+            if (lane == 0) red[c][wid] = sum;
+        }
+        __syncthreads();
+        if (tid < NC) {
+            double sum = 0.;
+            for (int k = 0; k < GM_WARPS; k++) sum = __dadd_rn(sum, red[tid][k]);
+            const float norm = fsqrt(__double2float_rn(sum));                                   // compute.c:205
+            F.norms[tid] = norm;
+            F.norms[4 + tid] = __frcp_rn(norm);                                                 // shared reciprocal for k_project
+        }
+        if (tid == 0) *F.counter = 0u;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side launcher
+// ------------------------------------------------------------------------------------------
+// Band height: one resident wave of CTAs if the frame allows it (long bands amortise the two
+// extra source rows each band recomputes), never fewer than 8 rows per band.
+static int g_grad_slots = 0;   // CTAs resident on the whole device, set by configure_kernels()
+
+void grad_geometry(int W, int H, int *ctas_x, int *bands, int *band_rows) {
+    const int strips = (W + GM_USE - 1) / GM_USE;
+    *ctas_x = (strips + GM_WARPS - 1) / GM_WARPS;
+    const int slots = g_grad_slots > 0 ? g_grad_slots : 148 * 3;
+    int want = slots / *ctas_x;
+    if (want < 1) want = 1;
+    int rows = (H + want - 1) / want;
+    if (rows < 8) rows = 8;
+    *band_rows = rows;
+    *bands = (H + rows - 1) / rows;
+}
+
+int grad_cta_count(int W, int H) {
+    // upper bound over every geometry grad_geometry can choose (bands of >= 8 rows)
+    const int strips = (W + GM_USE - 1) / GM_USE;
+    return ((strips + GM_WARPS - 1) / GM_WARPS) * ((H + 7) / 8);
+}
+
+cudaError_t configure_kernels() {
+    int per_sm = 0, dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gradient<3>, GM_NT, 0);
+    if (e != cudaSuccess) return e;
+    g_grad_slots = sms * (per_sm > 0 ? per_sm : 1);
+    return cudaSuccess;
+}
+
+cudaError_t launch_gradient(const FrameDev &F, float factor, cudaStream_t s) {
+    int cx, bands, rows;
+    grad_geometry(F.W, F.H, &cx, &bands, &rows);
+    dim3 grid(cx, bands);
+    switch (F.nc) {
+        case 1: k_gradient<1><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
+        case 2: k_gradient<2><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
+        default: k_gradient<3><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace j2p

@@ -1,7 +1,14 @@
 set -x
 export J2P_EXPECT_GPU=1
 mkdir -p gpurun_out
-./tools/divcheck 2>&1 | tee gpurun_out/divcheck.txt
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5
-python -m pytest tests -m gpu -x -q 2>&1 | tail -15
-python bench.py --steps 5 --warmup 3 > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; tail -c 1500 gpurun_out/bench_quick.json; tail -3 gpurun_out/bench_quick.err
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+python -m pytest tests -m gpu -x -q 2>&1 | tail -8
+python bench.py --steps 5 --warmup 3 > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench_quick.json'))
+print('value', d['value'], 'ms/step', d['ms_per_step'], 'e2e', d['e2e']['value'], d['e2e']['ms_per_step'])
+for k in d['roofline']['kernels']: print(k['name'], k['ms'], k['frac'])
+print('iter', d['roofline']['iteration'], 'clocks', d['clocks'], 'checksum', d['checksum'])
+PY
+tail -3 gpurun_out/bench_quick.err
+bash tools/run_profile_only.sh ${1:-x} > /dev/null 2>&1
