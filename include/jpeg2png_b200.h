@@ -90,8 +90,8 @@ int j2p_device_count(void);
 
 /* Describes one frame to solve: the planes that are optimised TOGETHER (reference joint mode:
  * nchannel = 3, jpeg2png.c:144; separate mode: three sessions with nchannel = 1, :147-152).
- * `row0`/`rows` select a horizontal strip of the frame for multi-GPU spatial tiling; pass
- * row0 = 0, rows = 0 for the whole frame. */
+ * A horizontal strip of the frame (multi-GPU spatial tiling) is selected at creation time with
+ * j2p_session_create_strip(). */
 struct j2p_frame_desc {
         unsigned nchannel;       /* 1..3 */
         unsigned plane_w[3];     /* coef->w  */
@@ -106,6 +106,31 @@ struct j2p_frame_desc {
 /* Create a session on `device` (cudaSetDevice ordinal).  Allocates all HBM working buffers. */
 int j2p_session_create(j2p_session **out, int device, const struct j2p_frame_desc *desc);
 void j2p_session_destroy(j2p_session *s);
+
+/* ---- row strips of one frame across several GPUs (BASELINE config 4) ------------
+ * A strip session holds frame rows [row0, row0+rows) of the frame described by `desc` (which
+ * always describes the WHOLE frame) plus two halo rows on every side that has a neighbour.
+ * row0 and row0+rows must be multiples of 8*h_samp of every plane (row0+rows may also be the
+ * frame height).  Uploads then carry only the coefficient rows of the strip.  One iteration is
+ *     j2p_session_gradient(s);                       k_gradient on the owned rows
+ *     <all-gather the 3 doubles at j2p_session_sums_ptr(s) over the ranks>
+ *     j2p_session_project(s, gathered, nranks);      fold in rank order -> norms, step + projection
+ *     <exchange halos: j2p_session_halo(s, c, side, &send, &recv, &count)>
+ * The driver (jpeg2png_b200/strips.py) does the two communication steps with torch.distributed
+ * (NCCL over NVLink on GPUs).  After (re)arming a strip session the driver exchanges the halos of
+ * the initial iterate once and calls j2p_session_copy_halo_to_prev(). */
+int j2p_session_create_strip(j2p_session **out, int device, const struct j2p_frame_desc *desc,
+                             unsigned row0, unsigned rows);
+int j2p_session_strip_info(const j2p_session *s, unsigned *local_rows, unsigned *first_owned,
+                           unsigned *owned_rows);
+int j2p_session_gradient(j2p_session *s);
+void *j2p_session_sums_ptr(j2p_session *s);
+int j2p_session_project(j2p_session *s, const double *sums_by_rank, unsigned nranks);
+/* side 0 = top, 1 = bottom.  send: first/last two owned rows of the current iterate; recv: the
+ * halo rows beyond them; count: floats to move (0 if there is no neighbour on that side). */
+int j2p_session_halo(j2p_session *s, unsigned channel, int side, void **send, void **recv,
+                     size_t *count);
+int j2p_session_copy_halo_to_prev(j2p_session *s);
 
 /* Working-frame size W x H = max over planes of (plane_w*w_samp, plane_h*h_samp) (compute.c:410-416). */
 unsigned j2p_session_width(const j2p_session *s);

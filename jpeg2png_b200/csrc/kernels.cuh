@@ -1,10 +1,12 @@
-// kernels.cuh — device-side parameter blocks shared by kernels.cu and session.cu.
+// kernels.cuh — device-side parameter blocks shared by the kernels and session.cu.
 #pragma once
 #include <stdint.h>
 
 namespace j2p {
 
-// One colour plane as the kernels see it.
+// One colour plane as the kernels see it.  For a strip session (multi-GPU row tiling) the
+// frame-sized buffers hold the strip's rows plus the halo rows, the coefficient-sized ones only
+// the strip's own coefficient rows.
 struct PlaneDev {
     float *x;             // current iterate x_k, H x W raster              (reference aux.fdata)
     float *xp;            // previous iterate x_{k-1}; receives x_{k+1}     (reference aux.fista)
@@ -12,16 +14,19 @@ struct PlaneDev {
     float *gp;            // DCT-distance gradient for the NEXT step at coefficient resolution,
                           // ch x cw raster: p_alpha * idct((cos - data*q)/q^2)   (compute.c:38-70)
     const int16_t *data;  // quantised coefficients, [blocks][64] natural order
-    int cw, ch;           // coefficient grid in samples
+    int cw, ch;           // coefficient grid in samples (ch: rows held by this session)
     int sw, sh;           // upsampling factors
-    int resample;         // !(cw == W && ch == H)                          (compute.c:338)
+    int resample;         // !(cw == W && ch == H) for the WHOLE frame      (compute.c:338)
     int use_prob;         // pweight != 0                                   (compute.c:244)
     float p_alpha;        // pweight*2*255*sqrtf(2)                         (compute.c:245)
     float cnt;            // (float)(sw*sh), the divisor of the block mean     (compute.c:359)
 };
 
 struct FrameDev {
-    int W, H, nc;
+    int W, H, nc;         // H: rows held locally (strip + halo rows); whole frame: H == Hg
+    int Hg;               // height of the whole frame
+    int y0g;              // frame row of local row 0
+    int t0, t1;           // local rows [t0, t1) this session owns (targets); the rest is halo
     PlaneDev pl[3];
     float q[3][64];       // quantisation tables as float
     float qq[3][64];      // q*q (fp32 product, compute.c:49)
@@ -31,9 +36,9 @@ struct FrameDev {
     int use_tgv;          // weight != 0                                    (compute.c:257)
     float step;           // radius / sqrtf(1 + iterations)                 (compute.c:425,443)
     double *partials;     // [3][grad_ctas] per-CTA sums of g^2
+    double *sums;         // [3] this session's sum of g^2 (strip mode: combined across ranks by the driver)
     float *norms;         // [0..2] sqrtf((float)sum g^2) (compute.c:200-206); [4..6] RN(1/norm)
     unsigned *counter;    // CTAs-done ticket for the last-CTA reduction
-    double *log_acc;      // [4][grad_ctas] optional objective partials (tv, tv2) + [3][proj] prob
     int grad_ctas;
 };
 

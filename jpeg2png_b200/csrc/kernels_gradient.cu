@@ -45,14 +45,18 @@ namespace j2p {
 // is set to 0, which makes every quotient of that pixel exactly 0.
 // ------------------------------------------------------------------------------------------
 constexpr int GM_WARPS = 4, GM_NT = GM_WARPS * 32, GM_USE = 60;
+#ifndef J2P_GRAD_MIN_CTAS
+#define J2P_GRAD_MIN_CTAS 3     // resident CTAs per SM the register allocation is bounded for (4 spills: measured slower)
+#endif
 
 template <int NC>
-__global__ void __launch_bounds__(GM_NT) k_gradient(const __grid_constant__ FrameDev F, const float factor, const int band_rows) {
+__global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient(const __grid_constant__ FrameDev F, const float factor, const int band_rows) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int W = F.W, H = F.H;
     const int X0 = (blockIdx.x * GM_WARPS + wid) * GM_USE;   // first target column of this warp
-    const int yb = blockIdx.y * band_rows;                   // first target row of this CTA
-    const int ye = min(yb + band_rows, H);
+    const int yb = F.t0 + blockIdx.y * band_rows;            // first target row of this CTA (local row index)
+    const int ye = min(yb + band_rows, F.t1);
+    const int s_last = F.Hg - 1 - F.y0g, s_first = -F.y0g;   // local indices of the frame's last / first row
     const int px0 = X0 - 2 + 2 * lane;                       // even; W is even => the pair is in or out together
     const bool pair_in = px0 >= 0 && px0 < W;
     const bool is_target = pair_in && lane >= 1 && lane <= 30;
@@ -82,33 +86,36 @@ __global__ void __launch_bounds__(GM_NT) k_gradient(const __grid_constant__ Fram
             gpx[c][k] = (F.pl[c].use_prob && pair_in && cx < F.pl[c].cw) ? cx : -1;
         }
 
+    // Rows/columns outside the frame are never consumed (their sources are dead, see above), so
+    // the loads are made unconditional by clamping the address into the frame: no branches.
+    const int pxc = pair_in ? px0 : 0;
     auto issue_row_loads = [&](int row) {
-        const bool ld = pair_in && row >= 0 && row < H;
-        if (ld) {
-            const size_t gi = (size_t)row * W + px0;
+        const int rc = min(max(row, 0), H - 1);
+        const size_t gi = (size_t)rc * W + pxc;
 #pragma unroll
-            for (int c = 0; c < NC; c++) {
-                ldx[c] = *reinterpret_cast<const float2 *>(F.pl[c].x + gi);
-                ldp[c] = *reinterpret_cast<const float2 *>(F.pl[c].xp + gi);
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < NC; c++) ldx[c] = ldp[c] = make_float2(0.f, 0.f);
+        for (int c = 0; c < NC; c++) {
+            ldx[c] = *reinterpret_cast<const float2 *>(F.pl[c].x + gi);
+            ldp[c] = *reinterpret_cast<const float2 *>(F.pl[c].xp + gi);
         }
     };
-    auto issue_gp_loads = [&](int row) {
+    // coefficient-grid row of the next target row, tracked incrementally (no per-step division)
+    int gcy[NC], grem[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        const int r0 = yb - F.t0;                   // coefficient rows are stored from the first owned row
+        gcy[c] = r0 / F.pl[c].sh;
+        grem[c] = r0 - gcy[c] * F.pl[c].sh;
+    }
+    auto issue_gp_loads = [&]() {       // for target rows yb, yb+1, ... in order
 #pragma unroll
         for (int c = 0; c < NC; c++) {
             const PlaneDev &P = F.pl[c];
-            pgp[c][0] = pgp[c][1] = 0.f;
-            if (P.use_prob && row >= 0) {
-                const int cy = row / P.sh;
-                if (cy < P.ch) {
-                    const float *gr = P.gp + (size_t)cy * P.cw;
-                    if (gpx[c][0] >= 0) pgp[c][0] = gr[gpx[c][0]];
-                    if (gpx[c][1] >= 0) pgp[c][1] = gr[gpx[c][1]];
-                }
-            }
+            const bool rowok = gcy[c] < P.ch;
+            const float *gr = P.gp + (size_t)(rowok ? gcy[c] : 0) * P.cw;
+            const float v0 = gr[max(gpx[c][0], 0)], v1 = gr[max(gpx[c][1], 0)];
+            pgp[c][0] = (rowok && gpx[c][0] >= 0) ? v0 : 0.f;
+            pgp[c][1] = (rowok && gpx[c][1] >= 0) ? v1 : 0.f;
+            if (++grem[c] == P.sh) { grem[c] = 0; gcy[c]++; }
         }
     };
 
@@ -129,12 +136,12 @@ __global__ void __launch_bounds__(GM_NT) k_gradient(const __grid_constant__ Fram
                 gpv[c][1] = pgp[c][1];
             }
             if (i < ye + 1) issue_row_loads(i + 1);
-            if (i >= yb && i < ye) issue_gp_loads(i);              // consumed next step, where the target row is s = i
+            if (i >= yb && i < ye) issue_gp_loads();               // consumed next step, where the target row is s = i
 
             if (i >= yb - 1) {
                 const int s = i - 1;
                 const bool src_in = pair_in && s >= 0 && s < H;
-                if (s >= H - 1) {                                   // no row below: gy := 0 (compute.c:81)
+                if (s >= s_last) {                                  // no row below in the frame: gy := 0 (compute.c:81)
 #pragma unroll
                     for (int c = 0; c < NC; c++) { yN[c][0] = yP[c][0]; yN[c][1] = yP[c][1]; }
                 }
@@ -185,7 +192,7 @@ __global__ void __launch_bounds__(GM_NT) k_gradient(const __grid_constant__ Fram
                 // ---- source row s: second-order TGV (compute.c:136-183) ------------------------
                 float t2s0[NC][2], lr0[NC][2], ud0[NC][2], dg0[NC][2];
                 if (use_tgv && i >= yb) {
-                    if (s <= 0) {                                   // no row above: gxy, gyy := 0 (compute.c:141-143)
+                    if (s <= s_first) {                             // no row above in the frame: gxy, gyy := 0 (compute.c:141-143)
 #pragma unroll
                         for (int c = 0; c < NC; c++)
 #pragma unroll
@@ -347,6 +354,7 @@ __global__ void __launch_bounds__(GM_NT) k_gradient(const __grid_constant__ Fram
             double sum = 0.;
             for (int k = 0; k < GM_WARPS; k++) sum = __dadd_rn(sum, red[tid][k]);
             const float norm = fsqrt(__double2float_rn(sum));                                   // compute.c:205
+            F.sums[tid] = sum;                                                                  // strip mode: combined across ranks
             F.norms[tid] = norm;
             F.norms[4 + tid] = __frcp_rn(norm);                                                 // shared reciprocal for k_project
         }
@@ -379,9 +387,13 @@ int grad_cta_count(int W, int H) {
     return ((strips + GM_WARPS - 1) / GM_WARPS) * ((H + 7) / 8);
 }
 
+cudaError_t configure_project_kernels();
+
 cudaError_t configure_kernels() {
     int per_sm = 0, dev = 0, sms = 0;
-    cudaError_t e = cudaGetDevice(&dev);
+    cudaError_t e = configure_project_kernels();
+    if (e != cudaSuccess) return e;
+    e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
@@ -393,7 +405,7 @@ cudaError_t configure_kernels() {
 
 cudaError_t launch_gradient(const FrameDev &F, float factor, cudaStream_t s) {
     int cx, bands, rows;
-    grad_geometry(F.W, F.H, &cx, &bands, &rows);
+    grad_geometry(F.W, F.t1 - F.t0, &cx, &bands, &rows);
     dim3 grid(cx, bands);
     switch (F.nc) {
         case 1: k_gradient<1><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;

@@ -1,11 +1,16 @@
 // kernels_project.cu — step + projection kernel, conventional decode, aux_init.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "kernels.cuh"
 #include "numerics.cuh"
+#include "project_common.cuh"
 
 namespace j2p {
+
+cudaError_t configure_project_blk();
+cudaError_t launch_project_blk(const FrameDev &F, int c, float factor, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------
 // 8x8 block transposes among the 8 lanes that own one block (lane j holds row j).
@@ -15,41 +20,79 @@ namespace j2p {
 // ------------------------------------------------------------------------------------------
 constexpr int TILE_STRIDE = 72;
 
-__device__ __forceinline__ void rows_to_cols(float (&v)[8], float *tile, int j) {
+__device__ __forceinline__ void rows_to_cols(float (&v)[8], float *tile, int j, unsigned mask = 0xffffffffu) {
     const int h = (j >> 2) & 1;
     float4 *row = reinterpret_cast<float4 *>(tile + j * 8);
     row[h] = make_float4(v[0], v[1], v[2], v[3]);
     row[h ^ 1] = make_float4(v[4], v[5], v[6], v[7]);
-    __syncwarp();
+    __syncwarp(mask);
 #pragma unroll
     for (int i = 0; i < 8; i++) v[i] = tile[i * 8 + (j ^ (((i >> 2) & 1) << 2))];
-    __syncwarp();
+    __syncwarp(mask);
 }
-__device__ __forceinline__ void cols_to_rows(float (&v)[8], float *tile, int j) {
+__device__ __forceinline__ void cols_to_rows(float (&v)[8], float *tile, int j, unsigned mask = 0xffffffffu) {
 #pragma unroll
     for (int i = 0; i < 8; i++) tile[i * 8 + (j ^ (((i >> 2) & 1) << 2))] = v[i];
-    __syncwarp();
+    __syncwarp(mask);
     const int h = (j >> 2) & 1;
     const float4 *row = reinterpret_cast<const float4 *>(tile + j * 8);
     const float4 lo = row[h], hi = row[h ^ 1];
     v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
     v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
-    __syncwarp();
+    __syncwarp(mask);
 }
 
 // 2-D transforms for a thread that holds row j of the block and ends holding row j.
 // Vertical pass first, horizontal second (ooura/dct.c:39-94, :103-158).
-__device__ __forceinline__ void fdct8x8_rows(float (&v)[8], float *tile, int j) {
-    rows_to_cols(v, tile, j);
+__device__ __forceinline__ void fdct8x8_rows(float (&v)[8], float *tile, int j, unsigned mask = 0xffffffffu) {
+    rows_to_cols(v, tile, j, mask);
     fdct8(v);
-    cols_to_rows(v, tile, j);
+    cols_to_rows(v, tile, j, mask);
     fdct8(v);
 }
-__device__ __forceinline__ void idct8x8_rows(float (&v)[8], float *tile, int j) {
-    rows_to_cols(v, tile, j);
+__device__ __forceinline__ void idct8x8_rows(float (&v)[8], float *tile, int j, unsigned mask = 0xffffffffu) {
+    rows_to_cols(v, tile, j, mask);
     idct8(v);
-    cols_to_rows(v, tile, j);
+    cols_to_rows(v, tile, j, mask);
     idct8(v);
+}
+// Two independent inverse transforms in lockstep (separate tiles, shared warp barriers): the
+// fp64 conversions of one fill the XU latency of the other.
+__device__ __forceinline__ void idct8x8_rows_x2(float (&a)[8], float (&b)[8], float *tile_a, float *tile_b, int j) {
+    const int h = (j >> 2) & 1;
+    {
+        float4 *ra = reinterpret_cast<float4 *>(tile_a + j * 8), *rb = reinterpret_cast<float4 *>(tile_b + j * 8);
+        ra[h] = make_float4(a[0], a[1], a[2], a[3]);
+        ra[h ^ 1] = make_float4(a[4], a[5], a[6], a[7]);
+        rb[h] = make_float4(b[0], b[1], b[2], b[3]);
+        rb[h ^ 1] = make_float4(b[4], b[5], b[6], b[7]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int o = i * 8 + (j ^ (((i >> 2) & 1) << 2));
+        a[i] = tile_a[o];
+        b[i] = tile_b[o];
+    }
+    __syncwarp();
+    idct8(a);
+    idct8(b);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int o = i * 8 + (j ^ (((i >> 2) & 1) << 2));
+        tile_a[o] = a[i];
+        tile_b[o] = b[i];
+    }
+    __syncwarp();
+    {
+        const float4 *ra = reinterpret_cast<const float4 *>(tile_a + j * 8), *rb = reinterpret_cast<const float4 *>(tile_b + j * 8);
+        const float4 al = ra[h], ah = ra[h ^ 1], bl = rb[h], bh = rb[h ^ 1];
+        a[0] = al.x; a[1] = al.y; a[2] = al.z; a[3] = al.w; a[4] = ah.x; a[5] = ah.y; a[6] = ah.z; a[7] = ah.w;
+        b[0] = bl.x; b[1] = bl.y; b[2] = bl.z; b[3] = bl.w; b[4] = bh.x; b[5] = bh.y; b[6] = bh.z; b[7] = bh.w;
+    }
+    __syncwarp();
+    idct8(a);
+    idct8(b);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -64,56 +107,59 @@ struct ProjPlane {
     int gx;         // CTAs per row
 };
 
-// the stepped point at one frame pixel: y = x + f (x - xp), then y - step * (g / norm)
-// (compute.c:436, :213).  `rn` = RN(1/norm) from k_gradient's last CTA.
-struct Stepper {
-    float factor, step, norm, rn;
-    bool stepping;
-    // IEEE division (generic / fallback paths)
-    __device__ __forceinline__ float operator()(float x, float xp, float g) const {
-        float y = fadd(x, fmul(factor, fsub(x, xp)));
-        if (stepping) y = fsub(y, fmul(step, fdiv(g, norm)));
-        return y;
-    }
-    // shared-reciprocal division; `key` collects the guard of numerics.cuh (smallest non-zero |g|)
-    __device__ __forceinline__ float fast(float x, float xp, float g, unsigned &key) const {
-        float y = fadd(x, fmul(factor, fsub(x, xp)));
-        if (stepping) {
-            key = min(key, qdiv_key(g));
-            y = fsub(y, fmul(step, qdiv_core(g, norm, rn)));
-        }
-        return y;
-    }
-};
+#ifndef J2P_PROJ_MIN_CTAS
+#define J2P_PROJ_MIN_CTAS 4     // resident CTAs per SM for full-resolution planes (register bound 64)
+#endif
 
 template <int SW, int SH>
-__global__ void __launch_bounds__(P_NT, (SW * SH <= 1) ? 4 : 2) k_project(const __grid_constant__ FrameDev F, const ProjPlane G, const float factor) {
+__global__ void __launch_bounds__(P_NT, (SW * SH <= 1) ? J2P_PROJ_MIN_CTAS : 2) k_project(const __grid_constant__ FrameDev F, const ProjPlane G, const float factor) {
     __shared__ __align__(16) float tiles[2][P_NT / 8][TILE_STRIDE];
     __shared__ __align__(16) float sq[3][64];          // q, q*q, RN(1/(q*q)) of this plane
+    __shared__ float snorm[2];                         // norm of g, RN(1/norm)   (from k_gradient)
     const int tid = threadIdx.x;
     const int c = G.c;
     const PlaneDev &P = F.pl[c];
-    if (tid < 64) {
-        sq[0][tid] = F.q[c][tid];
-        sq[1][tid] = F.qq[c][tid];
-        sq[2][tid] = F.rqq[c][tid];
-    }
-    __syncthreads();
-    const int ctay = blockIdx.x / G.gx, ctax = blockIdx.x - ctay * G.gx;
+    const int ctax = blockIdx.x, ctay = blockIdx.y;
     const int W = F.W, H = F.H;
     const int b = tid >> 3, j = tid & 7;
     const int bx = ctax * P_BW + (b & (P_BW - 1)), by = ctay * P_BH + (b >> 3);
     const bool real = bx < (P.cw >> 3) && by < (P.ch >> 3);
     const int sw = SW ? SW : P.sw, sh = SW ? SH : P.sh;
+    const int cy = by * 8 + j;
+
+    // Everything that comes from HBM is requested before the first wait: the coefficient row, for
+    // full-resolution planes the eight pixels of x_k, x_{k-1} and g, and (one thread) the norm.
+    int4 draw = make_int4(0, 0, 0, 0);
+    float4 ra[2], rp[2], rg[2];
+    if (real) {
+        draw = __ldg(reinterpret_cast<const int4 *>(P.data + ((size_t)(by * (P.cw >> 3) + bx) * 64 + j * 8)));
+        if constexpr (SW == 1 && SH == 1) {
+            const size_t gi = (size_t)cy * W + (size_t)bx * 8;
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                ra[k] = reinterpret_cast<const float4 *>(P.x + gi)[k];
+                rp[k] = reinterpret_cast<const float4 *>(P.xp + gi)[k];
+                rg[k] = reinterpret_cast<const float4 *>(P.g + gi)[k];
+            }
+        }
+    }
+    if (tid < 64) {
+        sq[0][tid] = F.q[c][tid];
+        sq[1][tid] = F.qq[c][tid];
+        sq[2][tid] = F.rqq[c][tid];
+    } else if (tid == 64) {
+        snorm[0] = F.norms[c];
+        snorm[1] = F.norms[4 + c];
+    }
+    __syncthreads();
     Stepper stepper;
     stepper.factor = factor;
     stepper.step = F.step;
-    stepper.norm = F.norms[c];
-    stepper.rn = F.norms[4 + c];
+    stepper.norm = snorm[0];
+    stepper.rn = snorm[1];
     stepper.stepping = stepper.norm != 0.f;                        // compute.c:211
     const bool norm_ok = qdiv_divisor_ok(stepper.norm);
     float *tileA = tiles[0][b], *tileB = tiles[1][b];
-    const int cy = by * 8 + j;
 
     if (!real) {
         // pixels of the frame that no coefficient block covers: step only (compute.c:349-350 never visits them)
@@ -129,9 +175,6 @@ __global__ void __launch_bounds__(P_NT, (SW * SH <= 1) ? 4 : 2) k_project(const 
         return;   // whole 8-lane groups leave together; the remaining lanes still __syncwarp among themselves
     }
 
-    // quantised coefficients of this row: issued first so the latency hides behind the pixel loads
-    const int4 draw = __ldg(reinterpret_cast<const int4 *>(P.data + ((size_t)(by * (P.cw >> 3) + bx) * 64 + j * 8)));
-
     // ---- stepped point of the footprint, block-row means (compute.c:348-370) ------------------
     constexpr int ZW = SW ? SW * 8 : 1, ZH = SW ? SH : 1;
     float z[ZH][ZW];
@@ -146,7 +189,12 @@ __global__ void __launch_bounds__(P_NT, (SW * SH <= 1) ? 4 : 2) k_project(const 
             const float4 *gr = reinterpret_cast<const float4 *>(P.g + gi);
 #pragma unroll
             for (int k = 0; k < SW * 2; k++) {
-                const float4 a = xr[k], p = pr[k], g = gr[k];
+                float4 a, p, g;
+                if constexpr (SW == 1 && SH == 1) {
+                    a = ra[k]; p = rp[k]; g = rg[k];
+                } else {
+                    a = xr[k]; p = pr[k]; g = gr[k];
+                }
                 z[sy][k * 4 + 0] = stepper.fast(a.x, p.x, g.x, key);
                 z[sy][k * 4 + 1] = stepper.fast(a.y, p.y, g.y, key);
                 z[sy][k * 4 + 2] = stepper.fast(a.z, p.z, g.z, key);
@@ -238,9 +286,12 @@ __global__ void __launch_bounds__(P_NT, (SW * SH <= 1) ? 4 : 2) k_project(const 
         for (int i = 0; i < 8; i++) r[i] = fdiv(num[i], qqv[i]);
     }
 
-    idct8x8_rows(v, tileA, j);
     if (P.use_prob) {
-        idct8x8_rows(r, tileB, j);
+        idct8x8_rows_x2(v, r, tileA, tileB, j);
+    } else {
+        idct8x8_rows(v, tileA, j);
+    }
+    if (P.use_prob) {
         float4 *gprow = reinterpret_cast<float4 *>(P.gp + (size_t)cy * P.cw + bx * 8);
         const float pa = P.p_alpha;                                          // compute.c:62 (the product)
         gprow[0] = make_float4(fmul(pa, r[0]), fmul(pa, r[1]), fmul(pa, r[2]), fmul(pa, r[3]));
@@ -324,21 +375,269 @@ __global__ void k_init_plane(const float *fdata, float *x, float *xp, int W, int
 }
 
 // ------------------------------------------------------------------------------------------
+// k_project_pipe — the full-resolution (1x1) plane, persistent and software-pipelined.
+//
+// Same arithmetic as k_project<1,1>.  What changes is the schedule: the transforms are bound by
+// the XU pipe (fp64 conversions, 16 per clock and SM; profiles/r01_microbench2.txt shows the
+// three transforms of a block sustain the XU limit when they run back to back), so XU must
+// never idle while a CTA waits for HBM or steps/clamps/stores.  Each CTA therefore loops over
+// tiles; every thread copies the 112 bytes it will need for the NEXT tile (its own row of x_k,
+// x_{k-1}, g and its coefficient row) into a private shared-memory slot with cp.async while it
+// works on the current one.  The slots are thread-private, so the loop has no block barrier and
+// the warps of an SM drift into different phases, which keeps all pipes busy.
+// ------------------------------------------------------------------------------------------
+constexpr int PP_SLOTS = 7;   // x lo/hi, xp lo/hi, g lo/hi, coefficient row
+constexpr size_t PP_DYN_SMEM = 2u * PP_SLOTS * P_NT * sizeof(float4);
+
+__global__ void __launch_bounds__(P_NT, 3) k_project_pipe(const __grid_constant__ FrameDev F, const ProjPlane G, const float factor,
+                                                           const int ntiles) {
+    extern __shared__ __align__(16) float4 stage[];              // [2][PP_SLOTS][P_NT]
+    __shared__ __align__(16) float tiles[P_NT / 8][TILE_STRIDE];
+    __shared__ __align__(16) float sq[3][64];
+    __shared__ float snorm[2];
+    const int tid = threadIdx.x;
+    const int c = G.c;
+    const PlaneDev &P = F.pl[c];
+    const int W = F.W, H = F.H;
+    const int b = tid >> 3, j = tid & 7;
+    const int bw = P.cw >> 3, bh = P.ch >> 3;
+
+    auto tile_block = [&](int t, int &bx, int &by) {
+        const int ctay = t / G.gx, ctax = t - ctay * G.gx;
+        bx = ctax * P_BW + (b & (P_BW - 1));
+        by = ctay * P_BH + (b >> 3);
+    };
+    auto issue = [&](int t, int st) {
+        int bx, by;
+        tile_block(t, bx, by);
+        if (bx < bw && by < bh) {
+            float4 *slot = stage + (size_t)st * PP_SLOTS * P_NT + tid;
+            const size_t gi = (size_t)(by * 8 + j) * W + (size_t)bx * 8;
+            cp_async16(slot + 0 * P_NT, P.x + gi);
+            cp_async16(slot + 1 * P_NT, P.x + gi + 4);
+            cp_async16(slot + 2 * P_NT, P.xp + gi);
+            cp_async16(slot + 3 * P_NT, P.xp + gi + 4);
+            cp_async16(slot + 4 * P_NT, P.g + gi);
+            cp_async16(slot + 5 * P_NT, P.g + gi + 4);
+            cp_async16(slot + 6 * P_NT, P.data + ((size_t)(by * bw + bx) * 64 + j * 8));
+        }
+        cp_async_commit();
+    };
+
+    int t = blockIdx.x;
+    if (t < ntiles) issue(t, 0);
+    if (tid < 64) {
+        sq[0][tid] = F.q[c][tid];
+        sq[1][tid] = F.qq[c][tid];
+        sq[2][tid] = F.rqq[c][tid];
+    } else if (tid == 64) {
+        snorm[0] = F.norms[c];
+        snorm[1] = F.norms[4 + c];
+    }
+    __syncthreads();
+    Stepper stepper;
+    stepper.factor = factor;
+    stepper.step = F.step;
+    stepper.norm = snorm[0];
+    stepper.rn = snorm[1];
+    stepper.stepping = stepper.norm != 0.f;                        // compute.c:211
+    const bool norm_ok = qdiv_divisor_ok(stepper.norm);
+    float *tile = tiles[b];
+    const unsigned gmask = 0xffu << (tid & 24);               // the 8 lanes that own this block
+    // this thread's rows of the three tables (constant over the tile loop)
+    float qv[8], qqv[8], rqv[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        qv[k] = sq[0][j * 8 + k];
+        qqv[k] = sq[1][j * 8 + k];
+        rqv[k] = sq[2][j * 8 + k];
+    }
+    const float pa = P.p_alpha;
+    const bool use_prob = P.use_prob != 0, resample = P.resample != 0;
+
+    for (int n = 0; t < ntiles; n++) {
+        const int tnext = t + gridDim.x;
+        if (tnext < ntiles) issue(tnext, (n + 1) & 1);
+        else cp_async_commit();
+        cp_async_wait<1>();                                        // the copies of tile t (this thread's own) have landed
+
+        int bx, by;
+        tile_block(t, bx, by);
+        t = tnext;
+        const int cy = by * 8 + j;
+        if (!(bx < bw && by < bh)) {
+            // pixels of the frame that no coefficient block covers: step only (compute.c:349-350 never visits them)
+            for (int i = 0; i < 8; i++) {
+                const int px = bx * 8 + i;
+                if (px < W && cy < H) {
+                    const size_t gi = (size_t)cy * W + px;
+                    P.xp[gi] = stepper(P.x[gi], P.xp[gi], P.g[gi]);
+                }
+            }
+            continue;      // whole 8-lane groups skip together; the warp barriers below are per 8-lane group
+        }
+        const float4 *slot = stage + (size_t)(n & 1) * PP_SLOTS * P_NT + tid;
+        float z[8];
+        {
+            unsigned key = 0xffffffffu;
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const float4 a = slot[(0 + k) * P_NT], p = slot[(2 + k) * P_NT], g = slot[(4 + k) * P_NT];
+                z[k * 4 + 0] = stepper.fast(a.x, p.x, g.x, key);
+                z[k * 4 + 1] = stepper.fast(a.y, p.y, g.y, key);
+                z[k * 4 + 2] = stepper.fast(a.z, p.z, g.z, key);
+                z[k * 4 + 3] = stepper.fast(a.w, p.w, g.w, key);
+            }
+            if (stepper.stepping && !(norm_ok && key >= QDIV_KEY_MIN)) {   // outside the proven range: IEEE division
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    const float4 a = slot[(0 + k) * P_NT], p = slot[(2 + k) * P_NT], g = slot[(4 + k) * P_NT];
+                    z[k * 4 + 0] = stepper(a.x, p.x, g.x);
+                    z[k * 4 + 1] = stepper(a.y, p.y, g.y);
+                    z[k * 4 + 2] = stepper(a.z, p.z, g.z);
+                    z[k * 4 + 3] = stepper(a.w, p.w, g.w);
+                }
+            }
+        }
+        const float4 dq = slot[6 * P_NT];
+        const int dw[4] = {__float_as_int(dq.x), __float_as_int(dq.y), __float_as_int(dq.z), __float_as_int(dq.w)};
+
+        float v[8], mean[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (resample) {                                        // sampling 1x1 but a coefficient grid smaller than the frame
+                const float m = fmul(fadd(0.f, z[i]), 1.0f);      // compute.c:351-359 with one sample: (0 + z) / 1
+                mean[i] = m;
+                v[i] = m;
+            } else {
+                mean[i] = 0.f;
+                v[i] = z[i];
+            }
+        }
+
+        fdct8x8_rows(v, tile, j, gmask);
+
+        // clamp to the quantisation interval (compute.c:323-331); DCT-distance residual (compute.c:47-49)
+        float r[8], num[8];
+        unsigned rkey = 0xffffffffu;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int di = (i & 1) ? (dw[i >> 1] >> 16) : (int)(short)(dw[i >> 1] & 0xffff);
+            const float d = (float)di;
+            const float q = qv[i];
+            const float lo = fmul(fsub(d, 0.5f), q), hi = fmul(fadd(d, 0.5f), q);
+            float tv = v[i];
+            tv = tv > hi ? hi : (tv < lo ? lo : tv);
+            v[i] = tv;
+            num[i] = fsub(tv, fmul(d, q));
+            rkey = min(rkey, qdiv_key(num[i]));
+            r[i] = qdiv_core(num[i], qqv[i], rqv[i]);
+        }
+        if (rkey < QDIV_KEY_MIN) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) r[i] = fdiv(num[i], qqv[i]);
+        }
+
+        idct8x8_rows(v, tile, j, gmask);
+        if (use_prob) {
+            idct8x8_rows(r, tile, j, gmask);
+            float4 *gprow = reinterpret_cast<float4 *>(P.gp + (size_t)cy * P.cw + bx * 8);
+            gprow[0] = make_float4(fmul(pa, r[0]), fmul(pa, r[1]), fmul(pa, r[2]), fmul(pa, r[3]));   // compute.c:62 (the product)
+            gprow[1] = make_float4(fmul(pa, r[4]), fmul(pa, r[5]), fmul(pa, r[6]), fmul(pa, r[7]));
+        }
+
+        // write x_{k+1} over x_{k-1} (compute.c:387-403)
+        float4 *o = reinterpret_cast<float4 *>(P.xp + (size_t)cy * W + (size_t)bx * 8);
+        if (resample) {
+            float e[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) e[i] = fadd(fsub(z[i], mean[i]), v[i]);
+            o[0] = make_float4(e[0], e[1], e[2], e[3]);
+            o[1] = make_float4(e[4], e[5], e[6], e[7]);
+        } else {
+            o[0] = make_float4(v[0], v[1], v[2], v[3]);
+            o[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------
-cudaError_t launch_project(const FrameDev &F, float factor, cudaStream_t s) {
+static int g_pipe_slots = 148 * 3;   // resident CTAs of k_project_pipe on the whole device
+// Which organisation projects a full-resolution plane: 0 = one thread per block (default),
+// 1 = 8 threads per block, persistent + cp.async, 2 = 8 threads per block, one tile per CTA.
+// (J2P_PROJ_VARIANT is a measurement aid for profiles/; all three are bit-identical.)
+static int g_proj_variant = 0;
+
+cudaError_t configure_project_kernels() {
+    if (const char *v = getenv("J2P_PROJ_VARIANT")) g_proj_variant = atoi(v);
+    cudaError_t e = configure_project_blk();
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_project_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PP_DYN_SMEM);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0, dev = 0, sms = 0;
+    e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_project_pipe, P_NT, PP_DYN_SMEM);
+    if (e != cudaSuccess) return e;
+    g_pipe_slots = sms * (per_sm > 0 ? per_sm : 1);
+    return cudaSuccess;
+}
+
+// strip sessions: fold the per-rank sums of g^2 in rank order (deterministic), then the norms of
+// compute.c:200-206 and their reciprocals
+__global__ void k_fold_sums(const double *sums_by_rank, int nranks, int nc, float *norms) {
+    const int c = threadIdx.x;
+    if (c >= nc) return;
+    double s = 0.;
+    for (int r = 0; r < nranks; r++) s = __dadd_rn(s, sums_by_rank[r * 3 + c]);
+    const float norm = fsqrt(__double2float_rn(s));
+    norms[c] = norm;
+    norms[4 + c] = __frcp_rn(norm);
+}
+
+cudaError_t launch_fold_sums(const double *sums_by_rank, int nranks, int nc, float *norms, cudaStream_t s) {
+    k_fold_sums<<<1, 32, 0, s>>>(sums_by_rank, nranks, nc, norms);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_project(const FrameDev &Fin, float factor, cudaStream_t s) {
+    // the projection is block-local: it only sees the rows the session owns (no halo rows)
+    FrameDev F = Fin;
+    if (F.t0 != 0 || F.t1 != F.H) {
+        const size_t off = (size_t)F.t0 * F.W;
+        for (int c = 0; c < F.nc; c++) {
+            F.pl[c].x += off;
+            F.pl[c].xp += off;
+            F.pl[c].g += off;
+        }
+        F.H = F.t1 - F.t0;
+    }
     for (int c = 0; c < F.nc; c++) {
         const PlaneDev &P = F.pl[c];
         const int tw = 8 * P_BW * P.sw, th = 8 * P_BH * P.sh;
         ProjPlane G;
         G.c = c;
         G.gx = (F.W + tw - 1) / tw;
-        const int total = G.gx * ((F.H + th - 1) / th);
-        if (P.sw == 1 && P.sh == 1) k_project<1, 1><<<total, P_NT, 0, s>>>(F, G, factor);
-        else if (P.sw == 2 && P.sh == 2) k_project<2, 2><<<total, P_NT, 0, s>>>(F, G, factor);
-        else if (P.sw == 2 && P.sh == 1) k_project<2, 1><<<total, P_NT, 0, s>>>(F, G, factor);
-        else if (P.sw == 1 && P.sh == 2) k_project<1, 2><<<total, P_NT, 0, s>>>(F, G, factor);
-        else k_project<0, 0><<<total, P_NT, 0, s>>>(F, G, factor);
+        const dim3 grid(G.gx, (F.H + th - 1) / th);
+        if (P.sw == 1 && P.sh == 1 && g_proj_variant == 0) {
+            const cudaError_t eb = launch_project_blk(F, c, factor, s);        // one thread per block (default)
+            if (eb != cudaSuccess) return eb;
+        } else if (P.sw == 1 && P.sh == 1 && g_proj_variant == 1) {
+            const int ntiles = (int)(grid.x * grid.y);
+            const int ctas = ntiles < g_pipe_slots ? ntiles : g_pipe_slots;
+            k_project_pipe<<<ctas, P_NT, PP_DYN_SMEM, s>>>(F, G, factor, ntiles);
+        } else if (P.sw == 1 && P.sh == 1) {
+            k_project<1, 1><<<grid, P_NT, 0, s>>>(F, G, factor);
+        }
+        else if (P.sw == 2 && P.sh == 2) k_project<2, 2><<<grid, P_NT, 0, s>>>(F, G, factor);
+        else if (P.sw == 2 && P.sh == 1) k_project<2, 1><<<grid, P_NT, 0, s>>>(F, G, factor);
+        else if (P.sw == 1 && P.sh == 2) k_project<1, 2><<<grid, P_NT, 0, s>>>(F, G, factor);
+        else k_project<0, 0><<<grid, P_NT, 0, s>>>(F, G, factor);
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }

@@ -30,6 +30,7 @@ int grad_cta_count(int W, int H);
 cudaError_t configure_kernels();
 cudaError_t launch_gradient(const FrameDev &F, float factor, cudaStream_t s);
 cudaError_t launch_project(const FrameDev &F, float factor, cudaStream_t s);
+cudaError_t launch_fold_sums(const double *sums_by_rank, int nranks, int nc, float *norms, cudaStream_t s);
 cudaError_t launch_decode(const int16_t *data, const float *q_dev, float *out, int cw, int ch, cudaStream_t s);
 cudaError_t launch_init_plane(const float *fdata, float *x, float *xp, int W, int H, int cw, int ch, int sw, int sh,
                               cudaStream_t s);
@@ -64,6 +65,8 @@ struct j2p_session {
     float *x[3] = {}, *xp[3] = {}, *g[3] = {}, *gp[3] = {}, *fdata0[3] = {}, *qdev[3] = {};
     int16_t *data[3] = {};
     bool uploaded[3] = {};
+    bool strip = false;       // row strip of a larger frame (multi-GPU tiling)
+    float pending_factor = 0.f;
     float t = 1.f;            // FISTA momentum state (compute.c:426)
     unsigned next_iter = 0;
     unsigned long long launches = 0;
@@ -89,7 +92,7 @@ extern "C" int j2p_device_count(void) {
 }
 
 extern "C" unsigned j2p_session_width(const j2p_session *s) { return s ? (unsigned)s->F.W : 0; }
-extern "C" unsigned j2p_session_height(const j2p_session *s) { return s ? (unsigned)s->F.H : 0; }
+extern "C" unsigned j2p_session_height(const j2p_session *s) { return s ? (unsigned)s->F.Hg : 0; }
 extern "C" void *j2p_session_stream(j2p_session *s) { return s ? (void *)s->stream : nullptr; }
 extern "C" void *j2p_session_plane_ptr(j2p_session *s, unsigned c) { return (s && c < (unsigned)s->F.nc) ? s->F.pl[c].x : nullptr; }
 extern "C" unsigned long long j2p_session_launches(const j2p_session *s) { return s ? s->launches : 0; }
@@ -102,14 +105,15 @@ extern "C" void j2p_session_destroy(j2p_session *s) {
         cudaFree(s->x[c]); cudaFree(s->xp[c]); cudaFree(s->g[c]); cudaFree(s->gp[c]);
         cudaFree(s->fdata0[c]); cudaFree(s->qdev[c]); cudaFree(s->data[c]);
     }
-    cudaFree(s->F.partials); cudaFree(s->F.norms); cudaFree(s->F.counter);
+    cudaFree(s->F.partials); cudaFree(s->F.norms); cudaFree(s->F.counter); cudaFree(s->F.sums);
     for (int i = 0; i < kEventRing; i++)
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
 
-static int create_impl(j2p_session *s, int device, const j2p_frame_desc *d) {
+// row0/rows select a horizontal strip of the frame (frame rows); rows == 0 means the whole frame.
+static int create_impl(j2p_session *s, int device, const j2p_frame_desc *d, unsigned row0, unsigned rows) {
     const int ndev = j2p_device_count();
     if (ndev <= 0) return fail(J2P_ERR_NODEVICE, "no CUDA device available (the solver has no CPU fallback)");
     if (device < 0 || device >= ndev) return fail(J2P_ERR_ARG, "device %d out of range (0..%d)", device, ndev - 1);
@@ -139,11 +143,29 @@ static int create_impl(j2p_session *s, int device, const j2p_frame_desc *d) {
     }
     if ((unsigned long long)W * H > 0x7fffffffull) return fail(J2P_ERR_ARG, "frame %ux%u too large", W, H);
     F.W = (int)W;
-    F.H = (int)H;
-    const size_t n = (size_t)W * H;
+    F.Hg = (int)H;
+    if (rows == 0) {        // whole-frame session: the local buffer is the frame
+        row0 = 0;
+        rows = H;
+    }
+    if (row0 + rows > H) return fail(J2P_ERR_ARG, "strip rows %u..%u exceed the frame height %u", row0, row0 + rows, H);
+    for (unsigned c = 0; c < d->nchannel; c++) {
+        const unsigned mcu = 8 * d->h_samp[c];
+        if (row0 % mcu || ((row0 + rows) % mcu && row0 + rows != H))
+            return fail(J2P_ERR_ARG, "strip rows %u..%u are not aligned to the %u-row blocks of plane %u", row0, row0 + rows, mcu, c);
+        if (d->plane_h[c] * d->h_samp[c] <= row0) return fail(J2P_ERR_ARG, "strip starts below the coefficient rows of plane %u", c);
+    }
+    // a strip carries two halo rows on every side that has a neighbour (the stencil reach)
+    const unsigned halo_top = row0 > 0 ? 2 : 0, halo_bot = row0 + rows < H ? 2 : 0;
+    s->strip = !(row0 == 0 && rows == H);
+    F.H = (int)(rows + halo_top + halo_bot);
+    F.y0g = (int)row0 - (int)halo_top;
+    F.t0 = (int)halo_top;
+    F.t1 = (int)(halo_top + rows);
+    const size_t n = (size_t)W * F.H;
 
     // scalars, evaluated on the host in the reference's own float expressions
-    const float radius = sqrtf((float)H * (float)W) / 2;                // compute.c:425
+    const float radius = sqrtf((float)H * (float)W) / 2;                // compute.c:425 (whole frame)
     F.step = radius / sqrtf((float)(1 + d->iterations));                // compute.c:443
     F.a1 = (float)(1. / (double)sqrtf((float)d->nchannel));             // compute.c:90
     const float tgv_alpha = d->weight / sqrtf((float)(4 / 2));          // compute.c:258
@@ -157,7 +179,11 @@ static int create_impl(j2p_session *s, int device, const j2p_frame_desc *d) {
     }
     for (unsigned c = 0; c < d->nchannel; c++) {
         PlaneDev &P = F.pl[c];
-        P.cw = (int)d->plane_w[c]; P.ch = (int)d->plane_h[c];
+        // coefficient rows this session holds: those whose footprint lies in the owned frame rows
+        const unsigned cy0 = row0 / d->h_samp[c];
+        unsigned cy1 = (row0 + rows + d->h_samp[c] - 1) / d->h_samp[c];
+        if (cy1 > d->plane_h[c]) cy1 = d->plane_h[c];
+        P.cw = (int)d->plane_w[c]; P.ch = (int)(cy1 - cy0);
         P.sw = (int)d->w_samp[c]; P.sh = (int)d->h_samp[c];
         P.resample = !(d->plane_w[c] == W && d->plane_h[c] == H);       // compute.c:338
         P.use_prob = d->pweight[c] != 0.f;                              // compute.c:244
@@ -173,9 +199,10 @@ static int create_impl(j2p_session *s, int device, const j2p_frame_desc *d) {
         CK(cudaMalloc(&s->qdev[c], 64 * sizeof(float)));
         P.x = s->x[c]; P.xp = s->xp[c]; P.g = s->g[c]; P.gp = s->gp[c]; P.data = s->data[c];
     }
-    F.grad_ctas = grad_cta_count(F.W, F.H);
+    F.grad_ctas = grad_cta_count(F.W, F.t1 - F.t0);
     CK(cudaMalloc(&F.partials, sizeof(double) * 3 * (size_t)F.grad_ctas));
     CK(cudaMalloc(&F.norms, sizeof(float) * 8));
+    CK(cudaMalloc(&F.sums, sizeof(double) * 4));
     CK(cudaMalloc(&F.counter, sizeof(unsigned)));
     CK(cudaMemsetAsync(F.counter, 0, sizeof(unsigned), s->stream));
     CK(cudaMemsetAsync(F.norms, 0, sizeof(float) * 8, s->stream));
@@ -183,10 +210,15 @@ static int create_impl(j2p_session *s, int device, const j2p_frame_desc *d) {
 }
 
 extern "C" int j2p_session_create(j2p_session **out, int device, const struct j2p_frame_desc *d) {
+    return j2p_session_create_strip(out, device, d, 0, 0);
+}
+
+extern "C" int j2p_session_create_strip(j2p_session **out, int device, const struct j2p_frame_desc *d, unsigned row0,
+                                        unsigned rows) {
     if (!out || !d) return fail(J2P_ERR_ARG, "null argument");
     *out = nullptr;
     j2p_session *s = new j2p_session();
-    const int rc = create_impl(s, device, d);
+    const int rc = create_impl(s, device, d, row0, rows);
     if (rc != J2P_OK) {
         char keep[sizeof g_err];
         memcpy(keep, g_err, sizeof keep);
@@ -206,7 +238,9 @@ static int reset_impl(j2p_session *s) {
         PlaneDev &P = F.pl[c];
         P.x = s->x[c];
         P.xp = s->xp[c];
-        CK(launch_init_plane(s->fdata0[c], P.x, P.xp, F.W, F.H, P.cw, P.ch, P.sw, P.sh, s->stream));
+        // owned rows only; a strip's halo rows are filled by the driver's first halo exchange
+        const size_t off = (size_t)F.t0 * F.W;
+        CK(launch_init_plane(s->fdata0[c], P.x + off, P.xp + off, F.W, F.t1 - F.t0, P.cw, P.ch, P.sw, P.sh, s->stream));
         s->launches++;
         // first step: cos == data*q exactly, so the DCT-distance gradient is exactly 0 (compute.c:283 vs :47)
         CK(cudaMemsetAsync(P.gp, 0, (size_t)P.cw * P.ch * sizeof(float), s->stream));
@@ -287,8 +321,82 @@ static int check_ready(j2p_session *s, unsigned first) {
     return J2P_OK;
 }
 
+// ---- strip sessions: one iteration in two halves, the driver combines sums and exchanges halos ----
+extern "C" int j2p_session_gradient(j2p_session *s) {
+    if (!s) return fail(J2P_ERR_ARG, "null session");
+    CK(cudaSetDevice(s->device));
+    for (int c = 0; c < s->F.nc; c++)
+        if (!s->uploaded[c]) return fail(J2P_ERR_ARG, "plane %d has not been uploaded", c);
+    // FISTA momentum (compute.c:431-432, :440), host floats
+    const float tnext = (1 + sqrtf(1 + 4 * (s->t * s->t))) / 2;
+    s->pending_factor = (s->t - 1) / tnext;
+    s->t = tnext;
+    CK(launch_gradient(s->F, s->pending_factor, s->stream));
+    s->launches++;
+    return J2P_OK;
+}
+
+extern "C" void *j2p_session_sums_ptr(j2p_session *s) { return s ? (void *)s->F.sums : nullptr; }
+
+extern "C" int j2p_session_project(j2p_session *s, const double *sums_by_rank, unsigned nranks) {
+    if (!s || !sums_by_rank || nranks == 0) return fail(J2P_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(s->device));
+    FrameDev &F = s->F;
+    CK(launch_fold_sums(sums_by_rank, (int)nranks, F.nc, F.norms, s->stream));
+    CK(launch_project(F, s->pending_factor, s->stream));
+    s->launches += 1 + (unsigned)F.nc;
+    for (int c = 0; c < F.nc; c++) {                                    // compute.c:438
+        float *tmp = F.pl[c].x;
+        F.pl[c].x = F.pl[c].xp;
+        F.pl[c].xp = tmp;
+    }
+    s->next_iter++;
+    return J2P_OK;
+}
+
+extern "C" int j2p_session_halo(j2p_session *s, unsigned c, int side, void **send, void **recv, size_t *count) {
+    if (!s || !send || !recv || !count) return fail(J2P_ERR_ARG, "null argument");
+    if (c >= (unsigned)s->F.nc || (side != 0 && side != 1)) return fail(J2P_ERR_ARG, "bad channel or side");
+    const FrameDev &F = s->F;
+    float *x = F.pl[c].x;
+    const size_t W = (size_t)F.W;
+    const bool has = side == 0 ? F.t0 > 0 : F.t1 < F.H;
+    *count = has ? 2 * W : 0;
+    if (side == 0) {
+        *send = x + (size_t)F.t0 * W;             // first two owned rows -> upper neighbour's bottom halo
+        *recv = x;                                // rows above the strip  <- upper neighbour's last two rows
+    } else {
+        *send = x + (size_t)(F.t1 - 2) * W;       // last two owned rows  -> lower neighbour's top halo
+        *recv = x + (size_t)F.t1 * W;
+    }
+    return J2P_OK;
+}
+
+extern "C" int j2p_session_copy_halo_to_prev(j2p_session *s) {
+    if (!s) return fail(J2P_ERR_ARG, "null session");
+    CK(cudaSetDevice(s->device));
+    const FrameDev &F = s->F;
+    const size_t W = (size_t)F.W;
+    for (int c = 0; c < F.nc; c++) {
+        if (F.t0 > 0) CK(cudaMemcpyAsync(F.pl[c].xp, F.pl[c].x, (size_t)F.t0 * W * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+        if (F.t1 < F.H)
+            CK(cudaMemcpyAsync(F.pl[c].xp + (size_t)F.t1 * W, F.pl[c].x + (size_t)F.t1 * W, (size_t)(F.H - F.t1) * W * sizeof(float),
+                               cudaMemcpyDeviceToDevice, s->stream));
+    }
+    return J2P_OK;
+}
+
+extern "C" int j2p_session_strip_info(const j2p_session *s, unsigned *local_rows, unsigned *first_owned, unsigned *owned_rows) {
+    if (!s) return fail(J2P_ERR_ARG, "null session");
+    if (local_rows) *local_rows = (unsigned)s->F.H;
+    if (first_owned) *first_owned = (unsigned)s->F.t0;
+    if (owned_rows) *owned_rows = (unsigned)(s->F.t1 - s->F.t0);
+    return J2P_OK;
+}
+
 extern "C" int j2p_session_iterate(j2p_session *s, unsigned first, unsigned n) {
     if (!s) return fail(J2P_ERR_ARG, "null session");
+    if (s->strip) return fail(J2P_ERR_ARG, "a strip session is driven with j2p_session_gradient / j2p_session_project");
     CK(cudaSetDevice(s->device));
     int rc = check_ready(s, first);
     if (rc != J2P_OK) return rc;
@@ -344,8 +452,9 @@ extern "C" int j2p_session_download(j2p_session *s, unsigned c, float *out) {
     if (!s || !out) return fail(J2P_ERR_ARG, "null argument");
     if (c >= (unsigned)s->F.nc) return fail(J2P_ERR_ARG, "channel %u out of range", c);
     CK(cudaSetDevice(s->device));
-    const size_t n = (size_t)s->F.W * s->F.H;
-    CK(cudaMemcpyAsync(out, s->F.pl[c].x, n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    // the rows this session owns (the whole frame, or the strip without its halo rows)
+    const size_t n = (size_t)s->F.W * (size_t)(s->F.t1 - s->F.t0);
+    CK(cudaMemcpyAsync(out, s->F.pl[c].x + (size_t)s->F.t0 * s->F.W, n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     return J2P_OK;
 }

@@ -1,0 +1,35 @@
+"""A/B timing aid: per-kernel device time of the bench workload for a given build of the library.
+usage: python tools/quick_time.py [lib.so ...]   (never a bench number; see bench.py)"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from jpeg2png_b200 import abi, synth  # noqa: E402
+
+libs = sys.argv[1:] or [abi.PRODUCT_LIB]
+img = synth.synth_coefs(3840, 2160, 50, '4:4:4', 1237)
+for path in libs:
+    lib = abi.declare_product(C.CDLL(path, mode=C.RTLD_LOCAL))
+    d = abi.FrameDesc()
+    d.nchannel = 3
+    for c, p in enumerate(img.planes):
+        d.plane_w[c], d.plane_h[c], d.w_samp[c], d.h_samp[c] = p.w, p.h, p.w_samp, p.h_samp
+        d.pweight[c] = 0.001
+    d.weight = 0.3
+    d.iterations = 100
+    s = C.c_void_p()
+    assert lib.j2p_session_create(C.byref(s), 0, C.byref(d)) == 0, lib.j2p_last_error()
+    for c, p in enumerate(img.planes):
+        data = np.ascontiguousarray(p.data)
+        quant = np.ascontiguousarray(p.quant)
+        assert lib.j2p_session_upload(s, c, data.ctypes.data, quant.ctypes.data, None) == 0
+    mg, mp = C.c_float(), C.c_float()
+    lib.j2p_session_profile(s, 10, C.byref(mg), C.byref(mp))
+    lib.j2p_session_profile(s, 40, C.byref(mg), C.byref(mp))
+    out = np.empty((2160, 3840), np.float32)
+    lib.j2p_session_download(s, 0, out.ctypes.data)
+    print(f'{os.path.basename(path):40s} gradient {mg.value*1e3:8.1f} us  project {mp.value*1e3:8.1f} us  sum {(mg.value+mp.value)*1e3:8.1f} us  checksum {float(np.float64(out).sum()):.6f}')
+    lib.j2p_session_destroy(s)

@@ -3,12 +3,5 @@ export J2P_EXPECT_GPU=1
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
-python bench.py --steps 5 --warmup 3 > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; python - <<'PY'
-import json
-d=json.load(open('gpurun_out/bench_quick.json'))
-print('value', d['value'], 'ms/step', d['ms_per_step'], 'e2e', d['e2e']['value'], d['e2e']['ms_per_step'])
-for k in d['roofline']['kernels']: print(k['name'], k['ms'], k['frac'])
-print('iter', d['roofline']['iteration'], 'clocks', d['clocks'], 'checksum', d['checksum'])
-PY
-tail -3 gpurun_out/bench_quick.err
+for v in 0 1 2; do J2P_PROJ_VARIANT=$v python tools/quick_time.py 2>&1 | tail -1; done
 bash tools/run_profile_only.sh ${1:-x} > /dev/null 2>&1
