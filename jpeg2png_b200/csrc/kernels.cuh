@@ -35,11 +35,15 @@ struct FrameDev {
     float a2;             // (float)(alpha*1./sqrtf(nc)), alpha = weight/sqrtf(2)   (compute.c:154,258)
     int use_tgv;          // weight != 0                                    (compute.c:257)
     float step;           // radius / sqrtf(1 + iterations)                 (compute.c:425,443)
-    double *partials;     // [3][grad_ctas] per-CTA sums of g^2
+    double *partials;     // [5][grad_ctas] per-CTA sums of g^2 (and, when logging, of the TV / TGV norms)
     double *sums;         // [3] this session's sum of g^2 (strip mode: combined across ranks by the driver)
     float *norms;         // [0..2] sqrtf((float)sum g^2) (compute.c:200-206); [4..6] RN(1/norm)
     unsigned *counter;    // CTAs-done ticket for the last-CTA reduction
     int grad_ctas;
+    // objective logging (compute.c:271-272), only when the caller asked for a CSV log
+    int log_on;
+    int log_slot;         // which of the two prob_dist slots k_project accumulates into
+    double *logsums;      // [0]=tv, [1]=tv2, [2+3*slot+c] = sum over plane c of (residual/q)^2
 };
 
 }  // namespace j2p

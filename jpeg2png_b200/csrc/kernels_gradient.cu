@@ -49,7 +49,9 @@ constexpr int GM_WARPS = 4, GM_NT = GM_WARPS * 32, GM_USE = 60;
 #define J2P_GRAD_MIN_CTAS 3     // resident CTAs per SM the register allocation is bounded for (4 spills: measured slower)
 #endif
 
-template <int NC>
+// LOG: additionally sum the objective terms the reference logs (compute.c:91,155: tv += alpha*norm
+// per pixel, fp64) — only instantiated for sessions with logging enabled (-c csv).
+template <int NC, bool LOG>
 __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient(const __grid_constant__ FrameDev F, const float factor, const int band_rows) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int W = F.W, H = F.H;
@@ -65,6 +67,7 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient(const __g
     const bool use_tgv = F.use_tgv != 0;
 
     double acc[NC];
+    double tv_acc = 0., tv2_acc = 0.;
     float yP[NC][2], gxP[NC][2], gyP[NC][2], ogp[NC][2], sv_tvb[NC][2], sv_ud[NC][2], sv_dg[NC][2];
     float2 ldx[NC], ldp[NC];      // x_k / x_{k-1} of the row after the one being formed
     float pgp[NC][2];             // DCT-distance term of the next target row
@@ -106,15 +109,19 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient(const __g
         gcy[c] = r0 / F.pl[c].sh;
         grem[c] = r0 - gcy[c] * F.pl[c].sh;
     }
+    unsigned pgp_ok = 0;                // bit c*2+k: the prefetched value is a real term (else the term is 0)
     auto issue_gp_loads = [&]() {       // for target rows yb, yb+1, ... in order
+        pgp_ok = 0;
 #pragma unroll
         for (int c = 0; c < NC; c++) {
             const PlaneDev &P = F.pl[c];
             const bool rowok = gcy[c] < P.ch;
             const float *gr = P.gp + (size_t)(rowok ? gcy[c] : 0) * P.cw;
-            const float v0 = gr[max(gpx[c][0], 0)], v1 = gr[max(gpx[c][1], 0)];
-            pgp[c][0] = (rowok && gpx[c][0] >= 0) ? v0 : 0.f;
-            pgp[c][1] = (rowok && gpx[c][1] >= 0) ? v1 : 0.f;
+            // raw loads only: nothing here may depend on the loaded values, or the prefetch would stall
+            pgp[c][0] = gr[max(gpx[c][0], 0)];
+            pgp[c][1] = gr[max(gpx[c][1], 0)];
+            if (rowok && gpx[c][0] >= 0) pgp_ok |= 1u << (c * 2);
+            if (rowok && gpx[c][1] >= 0) pgp_ok |= 2u << (c * 2);
             if (++grem[c] == P.sh) { grem[c] = 0; gcy[c]++; }
         }
     };
@@ -132,8 +139,8 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient(const __g
             float gpv[NC][2];
 #pragma unroll
             for (int c = 0; c < NC; c++) {
-                gpv[c][0] = pgp[c][0];
-                gpv[c][1] = pgp[c][1];
+                gpv[c][0] = (pgp_ok >> (c * 2)) & 1u ? pgp[c][0] : 0.f;
+                gpv[c][1] = (pgp_ok >> (c * 2)) & 2u ? pgp[c][1] : 0.f;
             }
             if (i < ye + 1) issue_row_loads(i + 1);
             if (i >= yb && i < ye) issue_gp_loads();               // consumed next step, where the target row is s = i
@@ -166,6 +173,7 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient(const __g
                 for (int k = 0; k < 2; k++) {
                     const float n = fsqrt(n1[k]);
                     const bool live = src_in && n != 0.f;                         // compute.c:97
+                    if (LOG && is_target && s >= yb && s < ye) tv_acc = __dadd_rn(tv_acc, (double)fmul(a1, n));   // compute.c:91
                     const float y = live ? __frcp_rn(n) : 0.f;
                     unsigned key = 0xffffffffu;
                     float num[NC][3];
@@ -221,6 +229,7 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient(const __g
                     for (int k = 0; k < 2; k++) {
                         const float n = fsqrt(n2[k]);
                         const bool live = src_in && n != 0.f;                     // compute.c:158
+                        if (LOG && is_target && s >= yb && s < ye) tv2_acc = __dadd_rn(tv2_acc, (double)fmul(a2, n));   // compute.c:155
                         const float y = live ? __frcp_rn(n) : 0.f;
                         unsigned key = 0xffffffffu;
                         float num[NC][4];
@@ -321,7 +330,7 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient(const __g
     }
 
     // CTA reduction (fixed order => run-to-run deterministic), then the last-CTA fold
-    __shared__ double red[3][GM_WARPS];
+    __shared__ double red[5][GM_WARPS];
     __shared__ unsigned ticket;
     const int tid = threadIdx.x;
 #pragma unroll
@@ -329,9 +338,13 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient(const __g
         const double sum = warp_sum(acc[c]);
         if (lane == 0) red[c][wid] = sum;
     }
+    if (LOG) {
+        const double a = warp_sum(tv_acc), b = warp_sum(tv2_acc);
+        if (lane == 0) { red[3][wid] = a; red[4][wid] = b; }
+    }
     __syncthreads();
     const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x, ncta = gridDim.x * gridDim.y;
-    if (tid < NC) {
+    if (tid < NC || (LOG && (tid == 3 || tid == 4))) {
         double sum = 0.;
         for (int k = 0; k < GM_WARPS; k++) sum = __dadd_rn(sum, red[tid][k]);
         F.partials[(size_t)tid * F.grad_ctas + cta] = sum;
@@ -357,6 +370,21 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient(const __g
             F.sums[tid] = sum;                                                                  // strip mode: combined across ranks
             F.norms[tid] = norm;
             F.norms[4 + tid] = __frcp_rn(norm);                                                 // shared reciprocal for k_project
+        }
+        if (LOG) {
+            __syncthreads();
+            for (int q = 3; q < 5; q++) {
+                double sum = 0.;
+                for (unsigned k = tid; k < ncta; k += GM_NT) sum = __dadd_rn(sum, __ldcg(&F.partials[(size_t)q * F.grad_ctas + k]));
+                sum = warp_sum(sum);
+                if (lane == 0) red[q][wid] = sum;
+            }
+            __syncthreads();
+            if (tid == 3 || tid == 4) {
+                double sum = 0.;
+                for (int k = 0; k < GM_WARPS; k++) sum = __dadd_rn(sum, red[tid][k]);
+                F.logsums[tid - 3] = sum;                                                          // tv, tv2
+            }
         }
         if (tid == 0) *F.counter = 0u;
     }
@@ -397,7 +425,7 @@ cudaError_t configure_kernels() {
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gradient<3>, GM_NT, 0);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gradient<3, false>, GM_NT, 0);
     if (e != cudaSuccess) return e;
     g_grad_slots = sms * (per_sm > 0 ? per_sm : 1);
     return cudaSuccess;
@@ -407,10 +435,18 @@ cudaError_t launch_gradient(const FrameDev &F, float factor, cudaStream_t s) {
     int cx, bands, rows;
     grad_geometry(F.W, F.t1 - F.t0, &cx, &bands, &rows);
     dim3 grid(cx, bands);
-    switch (F.nc) {
-        case 1: k_gradient<1><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
-        case 2: k_gradient<2><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
-        default: k_gradient<3><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
+    if (F.log_on) {
+        switch (F.nc) {
+            case 1: k_gradient<1, true><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
+            case 2: k_gradient<2, true><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
+            default: k_gradient<3, true><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
+        }
+    } else {
+        switch (F.nc) {
+            case 1: k_gradient<1, false><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
+            case 2: k_gradient<2, false><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
+            default: k_gradient<3, false><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
+        }
     }
     return cudaGetLastError();
 }

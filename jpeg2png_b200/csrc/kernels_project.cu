@@ -7,100 +7,25 @@
 #include "numerics.cuh"
 #include "project_common.cuh"
 
+#ifndef J2P_EXP
+#define J2P_EXP 0      // measurement aid (tools/): bit mask of phases to knock out in k_project<>; 0 in every real build
+#endif
+
 namespace j2p {
 
 cudaError_t configure_project_blk();
 cudaError_t launch_project_blk(const FrameDev &F, int c, float factor, cudaStream_t s);
-
-// ------------------------------------------------------------------------------------------
-// 8x8 block transposes among the 8 lanes that own one block (lane j holds row j).
-// tile: 8 rows x 8 floats; element (r, c) lives at r*8 + (c ^ (((r>>2)&1)<<2)) — the two float4
-// halves of rows 4..7 are swapped, which makes both the 128-bit row accesses and the scalar
-// column accesses bank-conflict free (tiles of the four blocks of a warp are 72 floats apart).
-// ------------------------------------------------------------------------------------------
-constexpr int TILE_STRIDE = 72;
-
-__device__ __forceinline__ void rows_to_cols(float (&v)[8], float *tile, int j, unsigned mask = 0xffffffffu) {
-    const int h = (j >> 2) & 1;
-    float4 *row = reinterpret_cast<float4 *>(tile + j * 8);
-    row[h] = make_float4(v[0], v[1], v[2], v[3]);
-    row[h ^ 1] = make_float4(v[4], v[5], v[6], v[7]);
-    __syncwarp(mask);
-#pragma unroll
-    for (int i = 0; i < 8; i++) v[i] = tile[i * 8 + (j ^ (((i >> 2) & 1) << 2))];
-    __syncwarp(mask);
-}
-__device__ __forceinline__ void cols_to_rows(float (&v)[8], float *tile, int j, unsigned mask = 0xffffffffu) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) tile[i * 8 + (j ^ (((i >> 2) & 1) << 2))] = v[i];
-    __syncwarp(mask);
-    const int h = (j >> 2) & 1;
-    const float4 *row = reinterpret_cast<const float4 *>(tile + j * 8);
-    const float4 lo = row[h], hi = row[h ^ 1];
-    v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
-    v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
-    __syncwarp(mask);
-}
-
-// 2-D transforms for a thread that holds row j of the block and ends holding row j.
-// Vertical pass first, horizontal second (ooura/dct.c:39-94, :103-158).
-__device__ __forceinline__ void fdct8x8_rows(float (&v)[8], float *tile, int j, unsigned mask = 0xffffffffu) {
-    rows_to_cols(v, tile, j, mask);
-    fdct8(v);
-    cols_to_rows(v, tile, j, mask);
-    fdct8(v);
-}
-__device__ __forceinline__ void idct8x8_rows(float (&v)[8], float *tile, int j, unsigned mask = 0xffffffffu) {
-    rows_to_cols(v, tile, j, mask);
-    idct8(v);
-    cols_to_rows(v, tile, j, mask);
-    idct8(v);
-}
-// Two independent inverse transforms in lockstep (separate tiles, shared warp barriers): the
-// fp64 conversions of one fill the XU latency of the other.
-__device__ __forceinline__ void idct8x8_rows_x2(float (&a)[8], float (&b)[8], float *tile_a, float *tile_b, int j) {
-    const int h = (j >> 2) & 1;
-    {
-        float4 *ra = reinterpret_cast<float4 *>(tile_a + j * 8), *rb = reinterpret_cast<float4 *>(tile_b + j * 8);
-        ra[h] = make_float4(a[0], a[1], a[2], a[3]);
-        ra[h ^ 1] = make_float4(a[4], a[5], a[6], a[7]);
-        rb[h] = make_float4(b[0], b[1], b[2], b[3]);
-        rb[h ^ 1] = make_float4(b[4], b[5], b[6], b[7]);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const int o = i * 8 + (j ^ (((i >> 2) & 1) << 2));
-        a[i] = tile_a[o];
-        b[i] = tile_b[o];
-    }
-    __syncwarp();
-    idct8(a);
-    idct8(b);
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const int o = i * 8 + (j ^ (((i >> 2) & 1) << 2));
-        tile_a[o] = a[i];
-        tile_b[o] = b[i];
-    }
-    __syncwarp();
-    {
-        const float4 *ra = reinterpret_cast<const float4 *>(tile_a + j * 8), *rb = reinterpret_cast<const float4 *>(tile_b + j * 8);
-        const float4 al = ra[h], ah = ra[h ^ 1], bl = rb[h], bh = rb[h ^ 1];
-        a[0] = al.x; a[1] = al.y; a[2] = al.z; a[3] = al.w; a[4] = ah.x; a[5] = ah.y; a[6] = ah.z; a[7] = ah.w;
-        b[0] = bl.x; b[1] = bl.y; b[2] = bl.z; b[3] = bl.w; b[4] = bh.x; b[5] = bh.y; b[6] = bh.z; b[7] = bh.w;
-    }
-    __syncwarp();
-    idct8(a);
-    idct8(b);
-}
+cudaError_t launch_project_tile(const FrameDev &F, int c, float factor, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------
 // k_project — 8 threads per coefficient block (thread j owns row j), 32 blocks per CTA.
 // Template <SW, SH>: compile-time sampling factors of the plane (float4 I/O, stepped values of
 // the whole footprint kept in registers); SW == 0 selects the run-time generic path.
 // ------------------------------------------------------------------------------------------
-constexpr int P_NT = 256, P_BW = 8, P_BH = 4;   // CTA tile: 8 x 4 coefficient blocks
+#ifndef J2P_PBW_LOG2
+#define J2P_PBW_LOG2 5     // CTA tile = 2^k blocks wide: 32 x 1 blocks = 1 KB contiguous per plane row (DRAM locality, profiles/r01_notes.md)
+#endif
+constexpr int P_NT = 256, P_BW = 1 << J2P_PBW_LOG2, P_BH = (P_NT / 8) / P_BW;   // CTA tile in coefficient blocks
 
 struct ProjPlane {
     int c;          // plane index
@@ -122,7 +47,7 @@ __global__ void __launch_bounds__(P_NT, (SW * SH <= 1) ? J2P_PROJ_MIN_CTAS : 2) 
     const int ctax = blockIdx.x, ctay = blockIdx.y;
     const int W = F.W, H = F.H;
     const int b = tid >> 3, j = tid & 7;
-    const int bx = ctax * P_BW + (b & (P_BW - 1)), by = ctay * P_BH + (b >> 3);
+    const int bx = ctax * P_BW + (b & (P_BW - 1)), by = ctay * P_BH + (b >> J2P_PBW_LOG2);
     const bool real = bx < (P.cw >> 3) && by < (P.ch >> 3);
     const int sw = SW ? SW : P.sw, sh = SW ? SH : P.sh;
     const int cy = by * 8 + j;
@@ -195,6 +120,13 @@ __global__ void __launch_bounds__(P_NT, (SW * SH <= 1) ? J2P_PROJ_MIN_CTAS : 2) 
                 } else {
                     a = xr[k]; p = pr[k]; g = gr[k];
                 }
+                if (J2P_EXP & 8) {
+                    z[sy][k * 4 + 0] = fadd(a.x, fadd(p.x, g.x));
+                    z[sy][k * 4 + 1] = fadd(a.y, fadd(p.y, g.y));
+                    z[sy][k * 4 + 2] = fadd(a.z, fadd(p.z, g.z));
+                    z[sy][k * 4 + 3] = fadd(a.w, fadd(p.w, g.w));
+                    continue;
+                }
                 z[sy][k * 4 + 0] = stepper.fast(a.x, p.x, g.x, key);
                 z[sy][k * 4 + 1] = stepper.fast(a.y, p.y, g.y, key);
                 z[sy][k * 4 + 2] = stepper.fast(a.z, p.z, g.z, key);
@@ -249,7 +181,7 @@ __global__ void __launch_bounds__(P_NT, (SW * SH <= 1) ? J2P_PROJ_MIN_CTAS : 2) 
         }
     }
 
-    fdct8x8_rows(v, tileA, j);
+    if (!(J2P_EXP & 1)) fdct8x8_rows(v, tileA, j);
 
     // ---- clamp to the quantisation interval (compute.c:323-331); DCT-distance residual ---------
     const int dw[4] = {draw.x, draw.y, draw.z, draw.w};
@@ -268,6 +200,10 @@ __global__ void __launch_bounds__(P_NT, (SW * SH <= 1) ? J2P_PROJ_MIN_CTAS : 2) 
     }
     float r[8], num[8];
     unsigned rkey = 0xffffffffu;
+    if (J2P_EXP & 2) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) { num[i] = 0.f; r[i] = fadd(v[i], qv[i] + (float)dw[i & 3]); }
+    } else {
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         const int di = (i & 1) ? (dw[i >> 1] >> 16) : (int)(short)(dw[i >> 1] & 0xffff);
@@ -285,12 +221,26 @@ __global__ void __launch_bounds__(P_NT, (SW * SH <= 1) ? J2P_PROJ_MIN_CTAS : 2) 
 #pragma unroll
         for (int i = 0; i < 8; i++) r[i] = fdiv(num[i], qqv[i]);
     }
+    if (F.log_on && P.use_prob) {
+        // objective term of the NEXT iteration: sum of (residual/q)^2 (compute_simd_step.c:22-26), fp64
+        double loc = 0.;
+#pragma unroll
+        for (int i = 0; i < 8; i++) loc = __dadd_rn(loc, (double)fsq(fdiv(num[i], qv[i])));
+        const unsigned gmask = 0xffu << (tid & 24);
+        loc = __dadd_rn(loc, __shfl_xor_sync(gmask, loc, 1));
+        loc = __dadd_rn(loc, __shfl_xor_sync(gmask, loc, 2));
+        loc = __dadd_rn(loc, __shfl_xor_sync(gmask, loc, 4));
+        if (j == 0) atomicAdd(&F.logsums[2 + 3 * F.log_slot + c], loc);
+    }
+    }
 
-    if (P.use_prob) {
+    if (J2P_EXP & 4) {
+    } else if (P.use_prob) {
         idct8x8_rows_x2(v, r, tileA, tileB, j);
     } else {
         idct8x8_rows(v, tileA, j);
     }
+    if ((J2P_EXP & 16) && v[0] != 123.456f) return;
     if (P.use_prob) {
         float4 *gprow = reinterpret_cast<float4 *>(P.gp + (size_t)cy * P.cw + bx * 8);
         const float pa = P.p_alpha;                                          // compute.c:62 (the product)
@@ -405,7 +355,7 @@ __global__ void __launch_bounds__(P_NT, 3) k_project_pipe(const __grid_constant_
     auto tile_block = [&](int t, int &bx, int &by) {
         const int ctay = t / G.gx, ctax = t - ctay * G.gx;
         bx = ctax * P_BW + (b & (P_BW - 1));
-        by = ctay * P_BH + (b >> 3);
+        by = ctay * P_BH + (b >> J2P_PBW_LOG2);
     };
     auto issue = [&](int t, int st) {
         int bx, by;
@@ -566,9 +516,12 @@ __global__ void __launch_bounds__(P_NT, 3) k_project_pipe(const __grid_constant_
 // host-side launchers
 // ------------------------------------------------------------------------------------------
 static int g_pipe_slots = 148 * 3;   // resident CTAs of k_project_pipe on the whole device
-// Which organisation projects a full-resolution plane: 0 = one thread per block (default),
-// 1 = 8 threads per block, persistent + cp.async, 2 = 8 threads per block, one tile per CTA.
-// (J2P_PROJ_VARIANT is a measurement aid for profiles/; all three are bit-identical.)
+// Which organisation projects a full-resolution plane:
+//   0 = 8 threads per block, coalesced swizzled staging (kernels_project_tile.cu)   [default]
+//   1 = 8 threads per block, persistent, thread-private cp.async staging
+//   2 = 8 threads per block, each thread fetches its own row
+//   3 = one thread per block, registers only (kernels_project_blk.cu)
+// J2P_PROJ_VARIANT is a measurement aid for profiles/; all four are bit-identical.
 static int g_proj_variant = 0;
 
 cudaError_t configure_project_kernels() {
@@ -624,8 +577,13 @@ cudaError_t launch_project(const FrameDev &Fin, float factor, cudaStream_t s) {
         G.c = c;
         G.gx = (F.W + tw - 1) / tw;
         const dim3 grid(G.gx, (F.H + th - 1) / th);
-        if (P.sw == 1 && P.sh == 1 && g_proj_variant == 0) {
-            const cudaError_t eb = launch_project_blk(F, c, factor, s);        // one thread per block (default)
+        if (F.log_on && P.sw == 1 && P.sh == 1) {
+            k_project<1, 1><<<grid, P_NT, 0, s>>>(F, G, factor);                // the variant that also sums the log terms
+        } else if (P.sw == 1 && P.sh == 1 && g_proj_variant == 0) {
+            const cudaError_t eb = launch_project_tile(F, c, factor, s);
+            if (eb != cudaSuccess) return eb;
+        } else if (P.sw == 1 && P.sh == 1 && g_proj_variant == 3) {
+            const cudaError_t eb = launch_project_blk(F, c, factor, s);
             if (eb != cudaSuccess) return eb;
         } else if (P.sw == 1 && P.sh == 1 && g_proj_variant == 1) {
             const int ntiles = (int)(grid.x * grid.y);

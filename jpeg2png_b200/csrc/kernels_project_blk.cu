@@ -237,6 +237,14 @@ __global__ void k_step_uncovered(const __grid_constant__ FrameDev F, const int c
     }
 }
 
+cudaError_t launch_step_uncovered(const FrameDev &F, int c, float factor, cudaStream_t s) {
+    const size_t n = (size_t)F.W * F.H;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_step_uncovered<<<blocks, 256, 0, s>>>(F, c, factor);
+    return cudaGetLastError();
+}
+
 static int g_blk_slots = 148 * 2;
 
 cudaError_t configure_project_blk() {
@@ -262,13 +270,7 @@ cudaError_t launch_project_blk(const FrameDev &F, int c, float factor, cudaStrea
     k_project_blk<<<ctas, PB_NT, PB_DYN_SMEM, s>>>(F, c, factor);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    if (P.cw < F.W || P.ch < F.H) {
-        const size_t n = (size_t)F.W * F.H;
-        int blocks = (int)((n + 255) / 256);
-        if (blocks > 148 * 8) blocks = 148 * 8;
-        k_step_uncovered<<<blocks, 256, 0, s>>>(F, c, factor);
-        e = cudaGetLastError();
-    }
+    if (P.cw < F.W || P.ch < F.H) e = launch_step_uncovered(F, c, factor, s);
     return e;
 }
 

@@ -36,4 +36,88 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+// ------------------------------------------------------------------------------------------
+// 8x8 block transposes among the 8 lanes that own one block (lane j holds row j).
+// tile: 8 rows x 8 floats; element (r, c) lives at r*8 + (c ^ (((r>>2)&1)<<2)) — the two float4
+// halves of rows 4..7 are swapped, which makes both the 128-bit row accesses and the scalar
+// column accesses bank-conflict free (tiles of the four blocks of a warp are 72 floats apart).
+// ------------------------------------------------------------------------------------------
+constexpr int TILE_STRIDE = 72;
+
+__device__ __forceinline__ void rows_to_cols(float (&v)[8], float *tile, int j, unsigned mask = 0xffffffffu) {
+    const int h = (j >> 2) & 1;
+    float4 *row = reinterpret_cast<float4 *>(tile + j * 8);
+    row[h] = make_float4(v[0], v[1], v[2], v[3]);
+    row[h ^ 1] = make_float4(v[4], v[5], v[6], v[7]);
+    __syncwarp(mask);
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = tile[i * 8 + (j ^ (((i >> 2) & 1) << 2))];
+    __syncwarp(mask);
+}
+__device__ __forceinline__ void cols_to_rows(float (&v)[8], float *tile, int j, unsigned mask = 0xffffffffu) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) tile[i * 8 + (j ^ (((i >> 2) & 1) << 2))] = v[i];
+    __syncwarp(mask);
+    const int h = (j >> 2) & 1;
+    const float4 *row = reinterpret_cast<const float4 *>(tile + j * 8);
+    const float4 lo = row[h], hi = row[h ^ 1];
+    v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+    v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+    __syncwarp(mask);
+}
+
+// 2-D transforms for a thread that holds row j of the block and ends holding row j.
+// Vertical pass first, horizontal second (ooura/dct.c:39-94, :103-158).
+__device__ __forceinline__ void fdct8x8_rows(float (&v)[8], float *tile, int j, unsigned mask = 0xffffffffu) {
+    rows_to_cols(v, tile, j, mask);
+    fdct8(v);
+    cols_to_rows(v, tile, j, mask);
+    fdct8(v);
+}
+__device__ __forceinline__ void idct8x8_rows(float (&v)[8], float *tile, int j, unsigned mask = 0xffffffffu) {
+    rows_to_cols(v, tile, j, mask);
+    idct8(v);
+    cols_to_rows(v, tile, j, mask);
+    idct8(v);
+}
+// Two independent inverse transforms in lockstep (separate tiles, shared warp barriers): the
+// fp64 conversions of one fill the XU latency of the other.
+__device__ __forceinline__ void idct8x8_rows_x2(float (&a)[8], float (&b)[8], float *tile_a, float *tile_b, int j) {
+    const int h = (j >> 2) & 1;
+    {
+        float4 *ra = reinterpret_cast<float4 *>(tile_a + j * 8), *rb = reinterpret_cast<float4 *>(tile_b + j * 8);
+        ra[h] = make_float4(a[0], a[1], a[2], a[3]);
+        ra[h ^ 1] = make_float4(a[4], a[5], a[6], a[7]);
+        rb[h] = make_float4(b[0], b[1], b[2], b[3]);
+        rb[h ^ 1] = make_float4(b[4], b[5], b[6], b[7]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int o = i * 8 + (j ^ (((i >> 2) & 1) << 2));
+        a[i] = tile_a[o];
+        b[i] = tile_b[o];
+    }
+    __syncwarp();
+    idct8(a);
+    idct8(b);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int o = i * 8 + (j ^ (((i >> 2) & 1) << 2));
+        tile_a[o] = a[i];
+        tile_b[o] = b[i];
+    }
+    __syncwarp();
+    {
+        const float4 *ra = reinterpret_cast<const float4 *>(tile_a + j * 8), *rb = reinterpret_cast<const float4 *>(tile_b + j * 8);
+        const float4 al = ra[h], ah = ra[h ^ 1], bl = rb[h], bh = rb[h ^ 1];
+        a[0] = al.x; a[1] = al.y; a[2] = al.z; a[3] = al.w; a[4] = ah.x; a[5] = ah.y; a[6] = ah.z; a[7] = ah.w;
+        b[0] = bl.x; b[1] = bl.y; b[2] = bl.z; b[3] = bl.w; b[4] = bh.x; b[5] = bh.y; b[6] = bh.z; b[7] = bh.w;
+    }
+    __syncwarp();
+    idct8(a);
+    idct8(b);
+}
+
+
 }  // namespace j2p

@@ -71,6 +71,9 @@ struct j2p_session {
     unsigned next_iter = 0;
     unsigned long long launches = 0;
     int logging = 0;
+    double log_host[8] = {};          // last device copy of logsums
+    long long log_host_iter = -1;     // iteration log_host belongs to
+    unsigned long long next_log_iter = 0;
     cudaEvent_t ev[kEventRing] = {};
     long long ev_iter[kEventRing];
 };
@@ -105,7 +108,7 @@ extern "C" void j2p_session_destroy(j2p_session *s) {
         cudaFree(s->x[c]); cudaFree(s->xp[c]); cudaFree(s->g[c]); cudaFree(s->gp[c]);
         cudaFree(s->fdata0[c]); cudaFree(s->qdev[c]); cudaFree(s->data[c]);
     }
-    cudaFree(s->F.partials); cudaFree(s->F.norms); cudaFree(s->F.counter); cudaFree(s->F.sums);
+    cudaFree(s->F.partials); cudaFree(s->F.norms); cudaFree(s->F.counter); cudaFree(s->F.sums); cudaFree(s->F.logsums);
     for (int i = 0; i < kEventRing; i++)
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -200,9 +203,13 @@ static int create_impl(j2p_session *s, int device, const j2p_frame_desc *d, unsi
         P.x = s->x[c]; P.xp = s->xp[c]; P.g = s->g[c]; P.gp = s->gp[c]; P.data = s->data[c];
     }
     F.grad_ctas = grad_cta_count(F.W, F.t1 - F.t0);
-    CK(cudaMalloc(&F.partials, sizeof(double) * 3 * (size_t)F.grad_ctas));
+    CK(cudaMalloc(&F.partials, sizeof(double) * 5 * (size_t)F.grad_ctas));
     CK(cudaMalloc(&F.norms, sizeof(float) * 8));
     CK(cudaMalloc(&F.sums, sizeof(double) * 4));
+    CK(cudaMalloc(&F.logsums, sizeof(double) * 8));
+    CK(cudaMemsetAsync(F.logsums, 0, sizeof(double) * 8, s->stream));
+    F.log_on = 0;
+    F.log_slot = 0;
     CK(cudaMalloc(&F.counter, sizeof(unsigned)));
     CK(cudaMemsetAsync(F.counter, 0, sizeof(unsigned), s->stream));
     CK(cudaMemsetAsync(F.norms, 0, sizeof(float) * 8, s->stream));
@@ -247,6 +254,9 @@ static int reset_impl(j2p_session *s) {
     }
     s->t = 1.f;
     s->next_iter = 0;
+    s->next_log_iter = 0;
+    s->log_host_iter = -1;
+    CK(cudaMemsetAsync(F.logsums, 0, sizeof(double) * 8, s->stream));    // iteration 0: DCT distance is exactly 0
     return J2P_OK;
 }
 
@@ -299,7 +309,17 @@ static int one_iteration(j2p_session *s, cudaEvent_t e0, cudaEvent_t e1, cudaEve
     if (e0) CK(cudaEventRecord(e0, s->stream));
     CK(launch_gradient(F, factor, s->stream));
     if (e1) CK(cudaEventRecord(e1, s->stream));
+    if (F.log_on) {
+        // k_project accumulates the DCT-distance objective of the NEXT iteration into the other slot
+        F.log_slot = (int)((s->next_log_iter + 1) & 1);
+        CK(cudaMemsetAsync(F.logsums + 2 + 3 * F.log_slot, 0, 3 * sizeof(double), s->stream));
+    }
     CK(launch_project(F, factor, s->stream));
+    if (F.log_on) {
+        CK(cudaMemcpyAsync(s->log_host, F.logsums, 8 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        s->log_host_iter = s->next_log_iter;
+        s->next_log_iter++;
+    }
     if (e2) CK(cudaEventRecord(e2, s->stream));
     s->launches += 1 + (unsigned)F.nc;
     for (int c = 0; c < F.nc; c++) {                                    // compute.c:438
@@ -468,11 +488,42 @@ extern "C" int j2p_session_sync(j2p_session *s) {
 
 extern "C" int j2p_session_set_logging(j2p_session *s, int enabled) {
     if (!s) return fail(J2P_ERR_ARG, "null session");
+    if (enabled && s->strip) return fail(J2P_ERR_ARG, "objective logging is not available on strip sessions");
     s->logging = enabled != 0;
+    s->F.log_on = s->logging;
     return J2P_OK;
 }
 
+// Objective terms of the most recently queued iteration, as the reference's SIMD build logs them
+// (compute.c:232-272, compute_simd_step.c:61): prob_dist = 0.5 * sum (residual/q)^2 over the
+// planes with pweight != 0, tv / tv2 = fp64 sums of alpha*norm, objective = their sum over the
+// float total_alpha.  Synchronises the session stream.
 extern "C" int j2p_session_objective(j2p_session *s, double out[4]) {
     if (!s || !out) return fail(J2P_ERR_ARG, "null argument");
-    return fail(J2P_ERR_ARG, "objective logging is not implemented yet");
+    if (!s->logging || s->log_host_iter < 0) return fail(J2P_ERR_ARG, "no logged iteration (call j2p_session_set_logging(s, 1) before iterating)");
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    const FrameDev &F = s->F;
+    const int slot = (int)(s->log_host_iter & 1);
+    double prob = 0.;
+    float total_alpha = 0.f;
+    for (int c = 0; c < F.nc; c++) {
+        if (F.pl[c].use_prob) {                                         // compute.c:244-247
+            total_alpha += F.pl[c].p_alpha;
+            prob += 0.5 * s->log_host[2 + 3 * slot + c];
+        }
+    }
+    total_alpha += (float)F.nc;                                         // compute.c:252
+    const double tv = s->log_host[0];
+    double tv2 = 0.;
+    if (F.use_tgv) {                                                    // compute.c:257-260
+        const float alpha = s->desc.weight / sqrtf((float)(4 / 2));
+        total_alpha += alpha * (float)F.nc;
+        tv2 = s->log_host[1];
+    }
+    out[0] = (tv + tv2 + prob) / (double)total_alpha;                   // compute.c:271
+    out[1] = prob;
+    out[2] = tv;
+    out[3] = tv2;
+    return J2P_OK;
 }

@@ -139,3 +139,88 @@ def test_session_reset_is_reproducible(lib):
         H.assert_bit_identical(runs[0], want, 'session vs oracle')
     finally:
         lib.j2p_session_destroy(s)
+
+
+def test_objective_log_matches_oracle(lib):
+    """-c csv path: the objective terms the reference logs every iteration (compute.c:271-272).
+    The sums are re-associated on the GPU, so this is a tolerance test (1e-9 relative on fp64 sums
+    of ~1e5 terms is far tighter than the reference's own C-vs-SIMD disagreement on prob_dist)."""
+    img = synth.synth_coefs(200, 136, 15, '4:2:0', seed=31)
+    f = H.decode_planes(img)
+    iters = 12
+    planes_o, log_o = H.run_compute('oracle', img, [0, 1, 2], 0.3, [0.001] * 3, iters, f, want_log=True)
+    d = abi.FrameDesc()
+    d.nchannel = 3
+    for c, p in enumerate(img.planes):
+        d.plane_w[c], d.plane_h[c], d.w_samp[c], d.h_samp[c] = p.w, p.h, p.w_samp, p.h_samp
+        d.pweight[c] = 0.001
+    d.weight = 0.3
+    d.iterations = iters
+    s = C.c_void_p()
+    assert lib.j2p_session_create(C.byref(s), 0, C.byref(d)) == 0, lib.j2p_last_error()
+    try:
+        assert lib.j2p_session_set_logging(s, 1) == 0
+        for c, p in enumerate(img.planes):
+            data = np.ascontiguousarray(p.data)
+            quant = np.ascontiguousarray(p.quant)
+            fd = np.ascontiguousarray(f[c])
+            assert lib.j2p_session_upload(s, c, data.ctypes.data, quant.ctypes.data, fd.ctypes.data) == 0
+        got = np.zeros((iters, 4))
+        for i in range(iters):
+            assert lib.j2p_session_iterate(s, i, 1) == 0, lib.j2p_last_error()
+            o = (C.c_double * 4)()
+            assert lib.j2p_session_objective(s, o) == 0, lib.j2p_last_error()
+            got[i] = list(o)
+        np.testing.assert_allclose(got, log_o, rtol=1e-9, atol=1e-12)
+        # logging must not change the iterate
+        W, H_ = lib.j2p_session_width(s), lib.j2p_session_height(s)
+        planes = []
+        for c in range(3):
+            out = np.empty((H_, W), np.float32)
+            assert lib.j2p_session_download(s, c, out.ctypes.data) == 0
+            planes.append(out)
+        H.assert_bit_identical(planes, planes_o, 'logged run vs oracle')
+    finally:
+        lib.j2p_session_destroy(s)
+
+
+def test_compute_callbacks_logger_and_progressbar(tmp_path):
+    """Drop-in contract of compute(): log->iteration / logger_log once per iteration when a CSV
+    log is open (compute.c:428, :271-272), progressbar_inc once per iteration (compute.c:449-452).
+    Runs in a child process because the callback library must be loaded before the solver."""
+    import subprocess
+    import sys
+    so = tmp_path / 'libcb.so'
+    subprocess.run(['/usr/bin/gcc', '-shared', '-fPIC', '-O1', '-o', str(so), os.path.join(os.path.dirname(__file__), 'cb_helper.c')], check=True)
+    code = f"""
+import ctypes as C, sys
+sys.path.insert(0, {H.ROOT!r})
+cb = C.CDLL({str(so)!r}, mode=C.RTLD_GLOBAL)
+import numpy as np
+from jpeg2png_b200 import abi, synth
+from tests import helpers as H
+lib = abi.load_product()
+img = synth.synth_coefs(96, 64, 20, '4:2:0', seed=9)
+f = H.decode_planes(img)
+_, want = H.run_compute('oracle', img, [0, 1, 2], 0.3, [0.001] * 3, 9, f, want_log=True)
+ca = abi.CoefArray(img, [0, 1, 2], f)
+libc = C.CDLL(None)
+libc.fopen.restype = C.c_void_p
+fh = libc.fopen(b'/dev/null', b'w')
+lg = abi.Logger(fh, b'x.jpg', 3, 0)
+pb = abi.ProgressBar(0, 9)
+pw = (C.c_float * 3)(0.001, 0.001, 0.001)
+lib.compute(3, ca.arr, C.byref(lg), C.byref(pb), C.c_float(0.3), pw, 9)
+assert cb.cb_log_count() == 9, cb.cb_log_count()
+assert cb.cb_progress_count() == 9 and pb.current == 9
+assert lg.iteration == 8
+cb.cb_get_row.argtypes = [C.c_uint, C.POINTER(C.c_double)]
+for i in range(9):
+    row = (C.c_double * 5)()
+    cb.cb_get_row(i, row)
+    assert int(row[0]) == i
+    np.testing.assert_allclose(list(row)[1:], want[i], rtol=1e-9, atol=1e-12)
+print('callbacks ok')
+"""
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True)
+    assert r.returncode == 0 and 'callbacks ok' in r.stdout, r.stdout + r.stderr
