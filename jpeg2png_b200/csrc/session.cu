@@ -21,6 +21,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <vector>
 
 #include "../../include/jpeg2png_b200.h"
 #include "kernels.cuh"
@@ -56,6 +57,56 @@ static int fail(int code, const char *fmt, ...) {
     } while (0)
 
 constexpr int kEventRing = 32;
+
+// ---- device memory: stream-ordered allocation from the device's default pool, which is told to
+// keep what it is given back (release threshold = max).  A compute() call therefore pays for
+// cudaMalloc only the first time a frame size is seen, and never for a device-wide cudaFree sync.
+static cudaError_t dev_alloc(void **p, size_t bytes, cudaStream_t st) { return cudaMallocAsync(p, bytes ? bytes : 16, st); }
+template <typename T>
+static cudaError_t dev_alloc(T **p, size_t bytes, cudaStream_t st) { return dev_alloc(reinterpret_cast<void **>(p), bytes, st); }
+static void dev_free(void *p, cudaStream_t st) {
+    if (p) cudaFreeAsync(p, st);
+}
+
+// ---- host <-> device staging for pageable caller memory (the reference's struct coef buffers are
+// malloc-family memory): 8 MB pinned chunks, double buffered, the pageable side copied with all
+// host threads (this also parallelises the first-touch page faults of a fresh result buffer).
+constexpr size_t kStageChunk = 8u << 20;
+struct PinnedPool {
+    std::mutex mu;
+    std::vector<void *> free_list;
+    void *get() {
+        {
+            std::lock_guard<std::mutex> l(mu);
+            if (!free_list.empty()) {
+                void *p = free_list.back();
+                free_list.pop_back();
+                return p;
+            }
+        }
+        void *p = nullptr;
+        if (cudaHostAlloc(&p, kStageChunk, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return p;
+    }
+    void put(void *p) {
+        std::lock_guard<std::mutex> l(mu);
+        free_list.push_back(p);
+    }
+};
+static PinnedPool g_pinned;
+
+static void par_memcpy(void *dst, const void *src, size_t bytes) {
+    const size_t piece = 1u << 20;
+    const long n = (long)((bytes + piece - 1) / piece);
+#pragma omp parallel for schedule(static) if (n > 2)
+    for (long i = 0; i < n; i++) {
+        const size_t off = (size_t)i * piece;
+        memcpy((char *)dst + off, (const char *)src + off, bytes - off < piece ? bytes - off : piece);
+    }
+}
 
 struct j2p_session {
     int device = 0;
@@ -105,10 +156,12 @@ extern "C" void j2p_session_destroy(j2p_session *s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (int c = 0; c < 3; c++) {
-        cudaFree(s->x[c]); cudaFree(s->xp[c]); cudaFree(s->g[c]); cudaFree(s->gp[c]);
-        cudaFree(s->fdata0[c]); cudaFree(s->qdev[c]); cudaFree(s->data[c]);
+        dev_free(s->x[c], s->stream); dev_free(s->xp[c], s->stream); dev_free(s->g[c], s->stream); dev_free(s->gp[c], s->stream);
+        dev_free(s->fdata0[c], s->stream); dev_free(s->qdev[c], s->stream); dev_free(s->data[c], s->stream);
     }
-    cudaFree(s->F.partials); cudaFree(s->F.norms); cudaFree(s->F.counter); cudaFree(s->F.sums); cudaFree(s->F.logsums);
+    dev_free(s->F.partials, s->stream); dev_free(s->F.norms, s->stream); dev_free(s->F.counter, s->stream);
+    dev_free(s->F.sums, s->stream); dev_free(s->F.logsums, s->stream);
+    if (s->stream) cudaStreamSynchronize(s->stream);
     for (int i = 0; i < kEventRing; i++)
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -128,7 +181,14 @@ static int create_impl(j2p_session *s, int device, const j2p_frame_desc *d, unsi
     CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail(J2P_ERR_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     if (device < 64) {
-        std::call_once(g_cfg_once[device], [&] { g_cfg_err[device] = configure_kernels(); });
+        std::call_once(g_cfg_once[device], [&] {
+            g_cfg_err[device] = configure_kernels();
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+        });
         CK(g_cfg_err[device]);
     } else {
         CK(configure_kernels());
@@ -193,24 +253,24 @@ static int create_impl(j2p_session *s, int device, const j2p_frame_desc *d, unsi
         P.p_alpha = d->pweight[c] * 2 * 255 * sqrtf(2);                 // compute.c:245
         P.cnt = (float)(d->w_samp[c] * d->h_samp[c]);                   // compute.c:359
         const size_t nc = (size_t)P.cw * P.ch;
-        CK(cudaMalloc(&s->x[c], n * sizeof(float)));
-        CK(cudaMalloc(&s->xp[c], n * sizeof(float)));
-        CK(cudaMalloc(&s->g[c], n * sizeof(float)));
-        CK(cudaMalloc(&s->gp[c], nc * sizeof(float)));
-        CK(cudaMalloc(&s->fdata0[c], nc * sizeof(float)));
-        CK(cudaMalloc(&s->data[c], nc * sizeof(int16_t)));
-        CK(cudaMalloc(&s->qdev[c], 64 * sizeof(float)));
+        CK(dev_alloc(&s->x[c], n * sizeof(float), s->stream));
+        CK(dev_alloc(&s->xp[c], n * sizeof(float), s->stream));
+        CK(dev_alloc(&s->g[c], n * sizeof(float), s->stream));
+        CK(dev_alloc(&s->gp[c], nc * sizeof(float), s->stream));
+        CK(dev_alloc(&s->fdata0[c], nc * sizeof(float), s->stream));
+        CK(dev_alloc(&s->data[c], nc * sizeof(int16_t), s->stream));
+        CK(dev_alloc(&s->qdev[c], 64 * sizeof(float), s->stream));
         P.x = s->x[c]; P.xp = s->xp[c]; P.g = s->g[c]; P.gp = s->gp[c]; P.data = s->data[c];
     }
     F.grad_ctas = grad_cta_count(F.W, F.t1 - F.t0);
-    CK(cudaMalloc(&F.partials, sizeof(double) * 5 * (size_t)F.grad_ctas));
-    CK(cudaMalloc(&F.norms, sizeof(float) * 8));
-    CK(cudaMalloc(&F.sums, sizeof(double) * 4));
-    CK(cudaMalloc(&F.logsums, sizeof(double) * 8));
+    CK(dev_alloc(&F.partials, sizeof(double) * 5 * (size_t)F.grad_ctas, s->stream));
+    CK(dev_alloc(&F.norms, sizeof(float) * 8, s->stream));
+    CK(dev_alloc(&F.sums, sizeof(double) * 4, s->stream));
+    CK(dev_alloc(&F.logsums, sizeof(double) * 8, s->stream));
     CK(cudaMemsetAsync(F.logsums, 0, sizeof(double) * 8, s->stream));
     F.log_on = 0;
     F.log_slot = 0;
-    CK(cudaMalloc(&F.counter, sizeof(unsigned)));
+    CK(dev_alloc(&F.counter, sizeof(unsigned), s->stream));
     CK(cudaMemsetAsync(F.counter, 0, sizeof(unsigned), s->stream));
     CK(cudaMemsetAsync(F.norms, 0, sizeof(float) * 8, s->stream));
     return J2P_OK;
@@ -266,6 +326,59 @@ extern "C" int j2p_session_reset(j2p_session *s) {
     return reset_impl(s);
 }
 
+// pageable host -> device through the pinned double buffer, on the session stream
+static int staged_h2d(j2p_session *s, void *dst, const void *src, size_t bytes) {
+    void *buf[2] = {g_pinned.get(), g_pinned.get()};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int rc = J2P_OK;
+    if (!buf[0] || !buf[1]) rc = fail(J2P_ERR_CUDA, "pinned staging allocation failed");
+    for (int k = 0; k < 2 && rc == J2P_OK; k++)
+        if (cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) != cudaSuccess) rc = fail(J2P_ERR_CUDA, "cudaEventCreate failed");
+    size_t off = 0;
+    for (int k = 0; off < bytes && rc == J2P_OK; k ^= 1) {
+        const size_t n = bytes - off < kStageChunk ? bytes - off : kStageChunk;
+        if (cudaEventSynchronize(ev[k]) != cudaSuccess) { rc = fail(J2P_ERR_CUDA, "cudaEventSynchronize failed"); break; }
+        par_memcpy(buf[k], (const char *)src + off, n);
+        if (cudaMemcpyAsync((char *)dst + off, buf[k], n, cudaMemcpyHostToDevice, s->stream) != cudaSuccess ||
+            cudaEventRecord(ev[k], s->stream) != cudaSuccess) { rc = fail(J2P_ERR_CUDA, "staged H2D copy failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        off += n;
+    }
+    for (int k = 0; k < 2; k++) {
+        if (ev[k]) { cudaEventSynchronize(ev[k]); cudaEventDestroy(ev[k]); }
+        if (buf[k]) g_pinned.put(buf[k]);
+    }
+    return rc;
+}
+
+// device -> pageable host, same scheme; returns when `dst` is complete
+static int staged_d2h(j2p_session *s, void *dst, const void *src, size_t bytes) {
+    void *buf[2] = {g_pinned.get(), g_pinned.get()};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int rc = J2P_OK;
+    if (!buf[0] || !buf[1]) rc = fail(J2P_ERR_CUDA, "pinned staging allocation failed");
+    for (int k = 0; k < 2 && rc == J2P_OK; k++)
+        if (cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) != cudaSuccess) rc = fail(J2P_ERR_CUDA, "cudaEventCreate failed");
+    const size_t nchunks = (bytes + kStageChunk - 1) / kStageChunk;
+    auto issue = [&](size_t i) -> bool {
+        const size_t off = i * kStageChunk, n = bytes - off < kStageChunk ? bytes - off : kStageChunk;
+        return cudaMemcpyAsync(buf[i & 1], (const char *)src + off, n, cudaMemcpyDeviceToHost, s->stream) == cudaSuccess &&
+               cudaEventRecord(ev[i & 1], s->stream) == cudaSuccess;
+    };
+    if (rc == J2P_OK && nchunks > 0 && !issue(0)) rc = fail(J2P_ERR_CUDA, "staged D2H copy failed");
+    for (size_t i = 0; i < nchunks && rc == J2P_OK; i++) {
+        if (i + 1 < nchunks && !issue(i + 1)) { rc = fail(J2P_ERR_CUDA, "staged D2H copy failed"); break; }
+        if (cudaEventSynchronize(ev[i & 1]) != cudaSuccess) { rc = fail(J2P_ERR_CUDA, "cudaEventSynchronize failed"); break; }
+        const size_t off = i * kStageChunk, n = bytes - off < kStageChunk ? bytes - off : kStageChunk;
+        par_memcpy((char *)dst + off, buf[i & 1], n);
+    }
+    cudaStreamSynchronize(s->stream);
+    for (int k = 0; k < 2; k++) {
+        if (ev[k]) cudaEventDestroy(ev[k]);
+        if (buf[k]) g_pinned.put(buf[k]);
+    }
+    return rc;
+}
+
 extern "C" int j2p_session_upload(j2p_session *s, unsigned c, const int16_t *data, const uint16_t *quant,
                                   const float *fdata) {
     if (!s || !data || !quant) return fail(J2P_ERR_ARG, "null argument");
@@ -283,9 +396,11 @@ extern "C" int j2p_session_upload(j2p_session *s, unsigned c, const int16_t *dat
         F.rqq[c][j] = (float)(1.0 / (double)F.qq[c][j]);                // RN(1/qq): fp64 quotient narrowed once is correctly rounded
     }
     CK(cudaMemcpyAsync(s->qdev[c], qf, sizeof qf, cudaMemcpyHostToDevice, s->stream));
-    CK(cudaMemcpyAsync(s->data[c], data, nc * sizeof(int16_t), cudaMemcpyHostToDevice, s->stream));
+    int rcs = staged_h2d(s, s->data[c], data, nc * sizeof(int16_t));
+    if (rcs != J2P_OK) return rcs;
     if (fdata) {
-        CK(cudaMemcpyAsync(s->fdata0[c], fdata, nc * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+        rcs = staged_h2d(s, s->fdata0[c], fdata, nc * sizeof(float));
+        if (rcs != J2P_OK) return rcs;
     } else {
         CK(launch_decode(s->data[c], s->qdev[c], s->fdata0[c], P.cw, P.ch, s->stream));
         s->launches++;
@@ -474,9 +589,7 @@ extern "C" int j2p_session_download(j2p_session *s, unsigned c, float *out) {
     CK(cudaSetDevice(s->device));
     // the rows this session owns (the whole frame, or the strip without its halo rows)
     const size_t n = (size_t)s->F.W * (size_t)(s->F.t1 - s->F.t0);
-    CK(cudaMemcpyAsync(out, s->F.pl[c].x + (size_t)s->F.t0 * s->F.W, n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
-    CK(cudaStreamSynchronize(s->stream));
-    return J2P_OK;
+    return staged_d2h(s, out, s->F.pl[c].x + (size_t)s->F.t0 * s->F.W, n * sizeof(float));
 }
 
 extern "C" int j2p_session_sync(j2p_session *s) {
