@@ -6,8 +6,10 @@
  * sm_100 device is usable this dies like every other fatal error of the reference
  * (utils.c:11-28: "jpeg2png: <message>" on stderr, exit(EXIT_FAILURE)).
  */
+#define _POSIX_C_SOURCE 199309L
 #include <stdarg.h>
 #include <stdio.h>
+#include <time.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -49,6 +51,13 @@ _Noreturn static void die(const char *msg, ...) {
         exit(EXIT_FAILURE);
 }
 
+/* J2P_TRACE=1: wall-clock of each phase of the call on stderr (a measurement aid, off by default) */
+static double now_ms(void) {
+        struct timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 /* how many iterations may be queued on the device ahead of the progress bar */
 #define J2P_PROGRESS_LAG 8u
 
@@ -74,8 +83,13 @@ void compute(unsigned nchannel, struct coef *coefs, struct logger *log, struct p
         const char *env = getenv("J2P_DEVICE");
         if (env && *env) device = atoi(env);
 
+        const char *trace_env = getenv("J2P_TRACE");
+        const int trace = trace_env && *trace_env == '1';
+        double t0 = trace ? now_ms() : 0, t1;
+
         j2p_session *s = NULL;
         if (j2p_session_create(&s, device, &d) != J2P_OK) die("%s", j2p_last_error());
+        if (trace) { t1 = now_ms(); fprintf(stderr, "j2p trace: create %.2f ms\n", t1 - t0); t0 = t1; }
         const int want_log = log && log->f != NULL;
         if (want_log && j2p_session_set_logging(s, 1) != J2P_OK) die("%s", j2p_last_error());
 
@@ -86,6 +100,7 @@ void compute(unsigned nchannel, struct coef *coefs, struct logger *log, struct p
                 coefs[c].fdata = NULL;
         }
 
+        if (trace) { t1 = now_ms(); fprintf(stderr, "j2p trace: upload %.2f ms\n", t1 - t0); t0 = t1; }
         unsigned reported = 0;
         for (unsigned i = 0; i < iterations; i++) {
                 if (log) log->iteration = i;                            /* compute.c:428 */
@@ -112,6 +127,11 @@ void compute(unsigned nchannel, struct coef *coefs, struct logger *log, struct p
                 }
         }
 
+        if (trace) {
+                t1 = now_ms(); fprintf(stderr, "j2p trace: queue %u iterations %.2f ms\n", iterations, t1 - t0); t0 = t1;
+                j2p_session_sync(s);
+                t1 = now_ms(); fprintf(stderr, "j2p trace: device drain %.2f ms\n", t1 - t0); t0 = t1;
+        }
         const unsigned w = j2p_session_width(s), h = j2p_session_height(s);
         for (unsigned c = 0; c < nchannel; c++) {                       /* compute.c:455-463 */
                 size_t bytes = (size_t)w * h * sizeof(float);
@@ -123,5 +143,7 @@ void compute(unsigned nchannel, struct coef *coefs, struct logger *log, struct p
                 coefs[c].w = w;
                 coefs[c].h = h;
         }
+        if (trace) { t1 = now_ms(); fprintf(stderr, "j2p trace: alloc + download %.2f ms\n", t1 - t0); t0 = t1; }
         j2p_session_destroy(s);
+        if (trace) { t1 = now_ms(); fprintf(stderr, "j2p trace: destroy %.2f ms\n", t1 - t0); }
 }

@@ -45,6 +45,9 @@ namespace j2p {
 // is set to 0, which makes every quotient of that pixel exactly 0.
 // ------------------------------------------------------------------------------------------
 constexpr int GM_WARPS = 4, GM_NT = GM_WARPS * 32, GM_USE = 60;
+#ifndef J2P_FAST_ROOTS
+#define J2P_FAST_ROOTS 0        // 1: sqrt_core / rcp_core instead of sqrt.rn / rcp.rn (needs tools/rootcheck to pass)
+#endif
 #ifndef J2P_GRAD_MIN_CTAS
 #define J2P_GRAD_MIN_CTAS 3     // resident CTAs per SM the register allocation is bounded for (4 spills: measured slower)
 #endif
@@ -171,10 +174,21 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient(const __g
                 }
 #pragma unroll
                 for (int k = 0; k < 2; k++) {
-                    const float n = fsqrt(n1[k]);
-                    const bool live = src_in && n != 0.f;                         // compute.c:97
+                    const float ssq = n1[k];
+                    float n, y;
+                    bool live, guard_ok;
+                    if (!LOG && J2P_FAST_ROOTS) {                                 // branch-free roots inside the guarded range (numerics.cuh)
+                        guard_ok = root_arg_ok(ssq);
+                        live = src_in && ssq != 0.f;                              // sqrtf(x) != 0  <=>  x != 0   (compute.c:97)
+                        n = guard_ok ? sqrt_core(ssq) : 1.f;
+                        y = (live && guard_ok) ? rcp_core(n) : 0.f;
+                    } else {
+                        n = fsqrt(ssq);
+                        live = src_in && n != 0.f;                                // compute.c:97
+                        y = live ? __frcp_rn(n) : 0.f;
+                        guard_ok = qdiv_divisor_ok(n);
+                    }
                     if (LOG && is_target && s >= yb && s < ye) tv_acc = __dadd_rn(tv_acc, (double)fmul(a1, n));   // compute.c:91
-                    const float y = live ? __frcp_rn(n) : 0.f;
                     unsigned key = 0xffffffffu;
                     float num[NC][3];
 #pragma unroll
@@ -187,7 +201,8 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient(const __g
                         tvr0[c][k] = qdiv_core(num[c][1], n, y);
                         tvb0[c][k] = qdiv_core(num[c][2], n, y);
                     }
-                    if (live && !(key >= QDIV_KEY_MIN && qdiv_divisor_ok(n))) {    // outside the proven range: IEEE division
+                    if (live && !(key >= QDIV_KEY_MIN && guard_ok)) {              // outside the proven range: IEEE square root and division
+                        n = fsqrt(ssq);
 #pragma unroll
                         for (int c = 0; c < NC; c++) {
                             tvs0[c][k] = fdiv(num[c][0], n);
@@ -227,10 +242,21 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient(const __g
                     }
 #pragma unroll
                     for (int k = 0; k < 2; k++) {
-                        const float n = fsqrt(n2[k]);
-                        const bool live = src_in && n != 0.f;                     // compute.c:158
+                        const float ssq = n2[k];
+                        float n, y;
+                        bool live, guard_ok;
+                        if (!LOG && J2P_FAST_ROOTS) {
+                            guard_ok = root_arg_ok(ssq);
+                            live = src_in && ssq != 0.f;                          // compute.c:158
+                            n = guard_ok ? sqrt_core(ssq) : 1.f;
+                            y = (live && guard_ok) ? rcp_core(n) : 0.f;
+                        } else {
+                            n = fsqrt(ssq);
+                            live = src_in && n != 0.f;                            // compute.c:158
+                            y = live ? __frcp_rn(n) : 0.f;
+                            guard_ok = qdiv_divisor_ok(n);
+                        }
                         if (LOG && is_target && s >= yb && s < ye) tv2_acc = __dadd_rn(tv2_acc, (double)fmul(a2, n));   // compute.c:155
-                        const float y = live ? __frcp_rn(n) : 0.f;
                         unsigned key = 0xffffffffu;
                         float num[NC][4];
 #pragma unroll
@@ -245,7 +271,8 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient(const __g
                             ud0[c][k] = qdiv_core(num[c][2], n, y);
                             dg0[c][k] = qdiv_core(num[c][3], n, y);
                         }
-                        if (live && !(key >= QDIV_KEY_MIN && qdiv_divisor_ok(n))) {
+                        if (live && !(key >= QDIV_KEY_MIN && guard_ok)) {
+                            n = fsqrt(ssq);
 #pragma unroll
                             for (int c = 0; c < NC; c++) {
                                 t2s0[c][k] = fdiv(num[c][0], n);

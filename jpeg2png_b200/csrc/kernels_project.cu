@@ -15,7 +15,7 @@ namespace j2p {
 
 cudaError_t configure_project_blk();
 cudaError_t launch_project_blk(const FrameDev &F, int c, float factor, cudaStream_t s);
-cudaError_t launch_project_tile(const FrameDev &F, int c, float factor, cudaStream_t s);
+cudaError_t launch_project_tile(const FrameDev &F, int c, int count, float factor, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------
 // k_project — 8 threads per coefficient block (thread j owns row j), 32 blocks per CTA.
@@ -580,8 +580,13 @@ cudaError_t launch_project(const FrameDev &Fin, float factor, cudaStream_t s) {
         if (F.log_on && P.sw == 1 && P.sh == 1) {
             k_project<1, 1><<<grid, P_NT, 0, s>>>(F, G, factor);                // the variant that also sums the log terms
         } else if (P.sw == 1 && P.sh == 1 && g_proj_variant == 0) {
-            const cudaError_t eb = launch_project_tile(F, c, factor, s);
+            int count = 1;      // following planes of identical geometry ride in the same launch (grid.z)
+            while (c + count < F.nc && F.pl[c + count].sw == 1 && F.pl[c + count].sh == 1 && F.pl[c + count].cw == P.cw &&
+                   F.pl[c + count].ch == P.ch)
+                count++;
+            const cudaError_t eb = launch_project_tile(F, c, count, factor, s);
             if (eb != cudaSuccess) return eb;
+            c += count - 1;
         } else if (P.sw == 1 && P.sh == 1 && g_proj_variant == 3) {
             const cudaError_t eb = launch_project_blk(F, c, factor, s);
             if (eb != cudaSuccess) return eb;

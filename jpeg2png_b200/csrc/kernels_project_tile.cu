@@ -24,7 +24,7 @@ namespace j2p {
 constexpr int PT_NT = 256;            // 32 blocks x 8 rows
 constexpr int PT_C4 = 64;             // float4 columns per tile row (256 pixels)
 
-__global__ void __launch_bounds__(PT_NT, 4) k_project_tile(const __grid_constant__ FrameDev F, const int c, const float factor) {
+__global__ void __launch_bounds__(PT_NT, 4) k_project_tile(const __grid_constant__ FrameDev F, const int c0, const float factor) {
     __shared__ __align__(16) float4 sx[8][PT_C4];                // x_k          -> later x_{k+1}
     __shared__ __align__(16) float4 sp[8][PT_C4];                // x_{k-1}      -> later gp
     __shared__ __align__(16) float4 sg[8][PT_C4];                // g
@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(PT_NT, 4) k_project_tile(const __grid_constant
     __shared__ __align__(16) float sq[3][64];
     __shared__ float snorm[2];
     const int tid = threadIdx.x;
+    const int c = c0 + blockIdx.z;                               // planes of equal geometry share one launch
     const PlaneDev &P = F.pl[c];
     const int W = F.W;
     const int bw = P.cw >> 3;
@@ -186,15 +187,16 @@ __global__ void __launch_bounds__(PT_NT, 4) k_project_tile(const __grid_constant
 
 cudaError_t launch_step_uncovered(const FrameDev &F, int c, float factor, cudaStream_t s);
 
-// F: already restricted to the rows the session owns (launch_project)
-cudaError_t launch_project_tile(const FrameDev &F, int c, float factor, cudaStream_t s) {
+// F: already restricted to the rows the session owns (launch_project).  Projects planes
+// c .. c+count-1, which must all be 1x1 planes with the same coefficient grid.
+cudaError_t launch_project_tile(const FrameDev &F, int c, int count, float factor, cudaStream_t s) {
     const PlaneDev &P = F.pl[c];
     const int bw = P.cw >> 3, bh = P.ch >> 3;
-    const dim3 grid((bw + 31) / 32, bh);
+    const dim3 grid((bw + 31) / 32, bh, count);
     k_project_tile<<<grid, PT_NT, 0, s>>>(F, c, factor);
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    if (P.cw < F.W || P.ch < F.H) e = launch_step_uncovered(F, c, factor, s);
+    for (int k = c; k < c + count && e == cudaSuccess; k++)
+        if (F.pl[k].cw < F.W || F.pl[k].ch < F.H) e = launch_step_uncovered(F, k, factor, s);
     return e;
 }
 
