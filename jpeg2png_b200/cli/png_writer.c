@@ -1,0 +1,74 @@
+/* png_writer.c — YCbCr float planes -> RGB PNG, without libpng (zlib only).
+ *
+ * Replaces reference png.c:20-78.  The colour conversion and quantisation to integer samples
+ * restate png.c:39-62 exactly (that is where "bit-identical PNG" is decided): double-precision
+ * YCbCr->RGB, clamp to [0,255] in double narrowed to float, scale by (1<<bits)/256 in float,
+ * TRUNCATE to unsigned; 16-bit samples big-endian.  Each plane is indexed with its own stride
+ * (png.c:39-41).  The container is a plain non-interlaced truecolour PNG: filter type 0 on every
+ * row, one zlib stream; pixels, not file bytes, are what must match a libpng-written file.
+ */
+#include "png_writer.h"
+
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+/* png.c:15-17: the argument is narrowed to float by the call, compared against double bounds */
+static float clamp255(float x) { return (float)((double)x > 255. ? 255. : ((double)x < 0. ? 0. : (double)x)); }
+
+void j2p_ycc_to_rgb(unsigned w, unsigned h, unsigned bits, const float *y, unsigned ys, const float *cb, unsigned cbs,
+                    const float *cr, unsigned crs, uint8_t *out, size_t out_stride) {
+        const unsigned depth = bits / 8;
+        const float bitfactor = (float)((double)(1 << bits) / 256.);                             /* png.c:43 */
+#pragma omp parallel for schedule(static)
+        for (unsigned i = 0; i < h; i++) {
+                uint8_t *row = out + (size_t)i * out_stride;
+                for (unsigned j = 0; j < w; j++) {
+                        const float yi = y[(size_t)i * ys + j], cbi = cb[(size_t)i * cbs + j], cri = cr[(size_t)i * crs + j];
+                        const unsigned r = (unsigned)(clamp255((double)yi + 1.402 * (double)cri) * bitfactor);                              /* png.c:44 */
+                        const unsigned g = (unsigned)(clamp255(((double)yi - 0.34414 * (double)cbi) - 0.71414 * (double)cri) * bitfactor);  /* png.c:45 */
+                        const unsigned b = (unsigned)(clamp255((double)yi + 1.772 * (double)cbi) * bitfactor);                              /* png.c:46 */
+                        uint8_t *px = row + (size_t)j * 3 * depth;
+                        if (bits == 8) {
+                                px[0] = r & 0xFF; px[1] = g & 0xFF; px[2] = b & 0xFF;
+                        } else {
+                                px[0] = (r >> 8) & 0xFF; px[1] = r & 0xFF;
+                                px[2] = (g >> 8) & 0xFF; px[3] = g & 0xFF;
+                                px[4] = (b >> 8) & 0xFF; px[5] = b & 0xFF;
+                        }
+                }
+        }
+}
+
+static int put_chunk(FILE *f, const char *type, const uint8_t *data, size_t len) {
+        uint8_t hdr[8] = {(uint8_t)(len >> 24), (uint8_t)(len >> 16), (uint8_t)(len >> 8), (uint8_t)len, (uint8_t)type[0], (uint8_t)type[1],
+                          (uint8_t)type[2], (uint8_t)type[3]};
+        uLong crc = crc32(0L, hdr + 4, 4);
+        if (len) crc = crc32(crc, data, (uInt)len);
+        const uint8_t tail[4] = {(uint8_t)(crc >> 24), (uint8_t)(crc >> 16), (uint8_t)(crc >> 8), (uint8_t)crc};
+        return fwrite(hdr, 1, 8, f) == 8 && (len == 0 || fwrite(data, 1, len, f) == len) && fwrite(tail, 1, 4, f) == 4 ? 0 : -1;
+}
+
+int j2p_write_png(FILE *out, unsigned w, unsigned h, unsigned bits, const float *y, unsigned ys, const float *cb, unsigned cbs,
+                  const float *cr, unsigned crs) {
+        if (bits != 8 && bits != 16) return -1;
+        const size_t row = (size_t)w * 3 * (bits / 8), stride = row + 1;      /* +1: filter-type byte */
+        uint8_t *raw = malloc(stride * h);
+        if (!raw) return -1;
+        for (unsigned i = 0; i < h; i++) raw[(size_t)i * stride] = 0;          /* filter 0 (None) */
+        j2p_ycc_to_rgb(w, h, bits, y, ys, cb, cbs, cr, crs, raw + 1, stride);
+        uLongf zlen = compressBound((uLong)(stride * h));
+        uint8_t *z = malloc(zlen);
+        int rc = -1;
+        if (z && compress2(z, &zlen, raw, (uLong)(stride * h), 6) == Z_OK) {
+                static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+                const uint8_t ihdr[13] = {(uint8_t)(w >> 24), (uint8_t)(w >> 16), (uint8_t)(w >> 8), (uint8_t)w, (uint8_t)(h >> 24), (uint8_t)(h >> 16),
+                                          (uint8_t)(h >> 8), (uint8_t)h, (uint8_t)bits, 2 /* truecolour */, 0, 0, 0};
+                if (fwrite(sig, 1, 8, out) == 8 && put_chunk(out, "IHDR", ihdr, 13) == 0 && put_chunk(out, "IDAT", z, zlen) == 0 &&
+                    put_chunk(out, "IEND", NULL, 0) == 0)
+                        rc = 0;
+        }
+        free(z);
+        free(raw);
+        return rc;
+}

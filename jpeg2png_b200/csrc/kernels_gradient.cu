@@ -46,7 +46,7 @@ namespace j2p {
 // ------------------------------------------------------------------------------------------
 constexpr int GM_WARPS = 4, GM_NT = GM_WARPS * 32, GM_USE = 60;
 #ifndef J2P_FAST_ROOTS
-#define J2P_FAST_ROOTS 0        // 1: sqrt_core / rcp_core instead of sqrt.rn / rcp.rn (needs tools/rootcheck to pass)
+#define J2P_FAST_ROOTS 1        // sqrt_core / rcp_core (numerics.cuh; exhaustively equal to sqrt.rn / rcp.rn, profiles/r01_rootcheck.txt); 0 = IEEE intrinsics
 #endif
 #ifndef J2P_GRAD_MIN_CTAS
 #define J2P_GRAD_MIN_CTAS 3     // resident CTAs per SM the register allocation is bounded for (4 spills: measured slower)

@@ -101,7 +101,9 @@ static PinnedPool g_pinned;
 static void par_memcpy(void *dst, const void *src, size_t bytes) {
     const size_t piece = 1u << 20;
     const long n = (long)((bytes + piece - 1) / piece);
-#pragma omp parallel for schedule(static) if (n > 2)
+    // four threads saturate the copy; a team as wide as the machine (128 hardware threads on the GPU
+    // boxes) spends two orders of magnitude longer waking up than copying (profiles/r01_notes.md)
+#pragma omp parallel for schedule(static) num_threads(4) if (n > 2)
     for (long i = 0; i < n; i++) {
         const size_t off = (size_t)i * piece;
         memcpy((char *)dst + off, (const char *)src + off, bytes - off < piece ? bytes - off : piece);
