@@ -131,6 +131,16 @@ def recorded_traffic(kernel):
         return None
 
 
+def emit(line, world):
+    """Rank 0's one JSON line.  Under torchrun on the GPU boxes the workers' stdout has been seen
+    arriving on the launcher's stderr (gpurun_out/bench_n2.* in round 1), so for N > 1 the same
+    line is written to both streams; the two copies are identical."""
+    text = json.dumps(line)
+    print(text, flush=True)
+    if world > 1:
+        print(text, file=sys.stderr, flush=True)
+
+
 def make_frame(seed):
     from jpeg2png_b200 import synth
     return synth.synth_coefs(WIDTH, HEIGHT, QUALITY, SUBSAMPLING, seed)
@@ -362,7 +372,7 @@ def run_product_arm(args, rank, local_rank, world):
             'cpu_baseline': cpu,
             'checksum': {'resident': checksum, 'e2e': e2e_checksum},
         }
-        print(json.dumps(line), flush=True)
+        emit(line, world)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -24,7 +24,12 @@ namespace j2p {
 constexpr int PT_NT = 256;            // 32 blocks x 8 rows
 constexpr int PT_C4 = 64;             // float4 columns per tile row (256 pixels)
 
-__global__ void __launch_bounds__(PT_NT, 4) k_project_tile(const __grid_constant__ FrameDev F, const int c0, const float factor) {
+#ifndef J2P_TILE_MIN_CTAS
+#define J2P_TILE_MIN_CTAS 4
+#endif
+// RES: the plane's coefficient grid is smaller than the frame (compute.c:338), e.g. 1080p luma
+template <bool RES>
+__global__ void __launch_bounds__(PT_NT, J2P_TILE_MIN_CTAS) k_project_tile(const __grid_constant__ FrameDev F, const int c0, const float factor) {
     __shared__ __align__(16) float4 sx[8][PT_C4];                // x_k          -> later x_{k+1}
     __shared__ __align__(16) float4 sp[8][PT_C4];                // x_{k-1}      -> later gp
     __shared__ __align__(16) float4 sg[8][PT_C4];                // g
@@ -75,7 +80,8 @@ __global__ void __launch_bounds__(PT_NT, 4) k_project_tile(const __grid_constant
     stepper.rn = snorm[1];
     stepper.stepping = stepper.norm != 0.f;                        // compute.c:211
     const bool norm_ok = qdiv_divisor_ok(stepper.norm);
-    const bool use_prob = P.use_prob != 0, resample = P.resample != 0;
+    const bool use_prob = P.use_prob != 0;
+    constexpr bool resample = RES;
     const unsigned gmask = 0xffu << (tid & 24);
     float *tile = tiles[b];
 
@@ -193,7 +199,8 @@ cudaError_t launch_project_tile(const FrameDev &F, int c, int count, float facto
     const PlaneDev &P = F.pl[c];
     const int bw = P.cw >> 3, bh = P.ch >> 3;
     const dim3 grid((bw + 31) / 32, bh, count);
-    k_project_tile<<<grid, PT_NT, 0, s>>>(F, c, factor);
+    if (P.resample) k_project_tile<true><<<grid, PT_NT, 0, s>>>(F, c, factor);
+    else k_project_tile<false><<<grid, PT_NT, 0, s>>>(F, c, factor);
     cudaError_t e = cudaGetLastError();
     for (int k = c; k < c + count && e == cudaSuccess; k++)
         if (F.pl[k].cw < F.W || F.pl[k].ch < F.H) e = launch_step_uncovered(F, k, factor, s);
