@@ -168,3 +168,34 @@ def test_png_writer_roundtrip(codecs, tmp_path):
         assert (rows[:, 0] == 0).all() and (rows[:, 1:].reshape(-1) == want).all()
         if bits == 8:
             assert (np.asarray(Image.open(path)).reshape(-1) == want).all()
+
+
+@pytest.mark.parametrize('w,h,sampling,ri', [
+    (64, 48, [(1, 1), (1, 1), (1, 1)], 0),
+    (70, 50, [(2, 2), (1, 1), (1, 1)], 0),          # 4:2:0, MCU padding dropped on the right and bottom
+    (70, 50, [(2, 2), (1, 1), (1, 1)], 3),          # restart interval
+    (95, 33, [(2, 1), (1, 1), (1, 1)], 5),          # 4:2:2 + restarts
+    (48, 40, [(4, 1), (2, 1), (1, 1)], 2),          # unusual factors: chroma planes with different sampling (w_samp 2 and 4)
+    (40, 72, [(1, 2), (1, 1), (1, 1)], 0),          # vertical-only subsampling
+])
+def test_reader_recovers_known_coefficients_exactly(codecs, w, h, sampling, ri):
+    """Files written by tests/jpeg_synth.py from KNOWN coefficients: exact round trip, natural
+    order, libjpeg's unpadded block grids, every sampling layout the reference accepts."""
+    from tests import jpeg_synth
+    planes, quants = jpeg_synth.random_planes(w, h, sampling, seed=w * 3 + h)
+    data = jpeg_synth.encode_baseline(w, h, sampling, planes, quants, restart_interval=ri)
+    assert Image.open(io.BytesIO(data)).size == (w, h)          # Pillow accepts the file too
+    maxh, maxv = max(s[0] for s in sampling), max(s[1] for s in sampling)
+    img, err = read_jpeg(codecs, data)
+    if any((h // (maxv // s[1]) + 7) // 8 != -(-(-(-h * s[1] // maxv)) // 8) or (w // (maxh // s[0]) + 7) // 8 != -(-(-(-w * s[0] // maxh)) // 8)
+           for s in sampling):
+        assert img is None and 'jpeg invalid coef' in err      # the reference's own size check (jpeg.c:59-64)
+        return
+    assert img is not None, err
+    for c, p in enumerate(img.planes):
+        wb, hb = -(-(-(-w * sampling[c][0] // maxh)) // 8), -(-(-(-h * sampling[c][1] // maxv)) // 8)
+        assert (p.w, p.h) == (wb * 8, hb * 8)
+        assert (p.w_samp, p.h_samp) == (maxh // sampling[c][0], maxv // sampling[c][1])
+        want = planes[c][:hb, :wb].reshape(-1)
+        assert (p.data == want).all()
+        assert (p.quant == quants[c]).all()

@@ -1,12 +1,6 @@
 export J2P_EXPECT_GPU=1
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=index,name --format=csv,noheader
-python -m pytest tests -m gpu -x -q 2>&1 | tail -6
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; python - <<'PY'
-import json
-try:
-    d=json.load(open('gpurun_out/bench_n2.json'))
-    print('N=2 value', d['value'], 'ms/step', d['ms_per_step'], 'e2e', d['e2e']['value'])
-except Exception as e:
-    print('bench n2 failed', e); print(open('gpurun_out/bench_n2.err').read()[-2000:])
-PY
+python tools/quick_time.py build_ab/lib_base.so build_ab/lib_cur.so build_ab/lib_g4.so build_ab/lib_t5.so build_ab/lib_t6.so 2>&1 | grep lib_
+J2P_TRACE=1 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_trace.json 2> gpurun_out/bench_trace.err
+grep -E "trace" gpurun_out/bench_trace.err | tail -14
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
