@@ -132,6 +132,20 @@ int j2p_session_halo(j2p_session *s, unsigned channel, int side, void **send, vo
                      size_t *count);
 int j2p_session_copy_halo_to_prev(j2p_session *s);
 
+/* Native strip loop: the same iteration with both exchanges queued on the session stream through
+ * NCCL (resolved at run time with dlopen("libnccl.so.2"); no link-time dependency), so the host
+ * never waits inside the loop.  One process per GPU: rank 0 obtains an id with
+ * j2p_comm_unique_id(), hands its 128 bytes to the other ranks by any means (the Python driver
+ * broadcasts it with torch.distributed), every rank calls j2p_comm_create().  Ranks are the strips
+ * in top-to-bottom order.  j2p_session_iterate_strip() is collective; its first call after
+ * (re)arming a session also exchanges the halos of the initial iterate. */
+typedef struct j2p_comm j2p_comm;
+#define J2P_COMM_ID_BYTES 128
+int j2p_comm_unique_id(void *out, size_t bytes);
+int j2p_comm_create(j2p_comm **out, int device, int nranks, int rank, const void *id, size_t bytes);
+void j2p_comm_destroy(j2p_comm *c);
+int j2p_session_iterate_strip(j2p_session *s, j2p_comm *c, unsigned n);
+
 /* Working-frame size W x H = max over planes of (plane_w*w_samp, plane_h*h_samp) (compute.c:410-416). */
 unsigned j2p_session_width(const j2p_session *s);
 unsigned j2p_session_height(const j2p_session *s);

@@ -642,3 +642,168 @@ extern "C" int j2p_session_objective(j2p_session *s, double out[4]) {
     out[3] = tv2;
     return J2P_OK;
 }
+
+// ---- native strip loop: NCCL on the session stream --------------------------------------------
+// The two exchanges of a strip iteration (all-gather of the three fp64 sums, neighbour exchange of
+// the two border rows) are enqueued from here, on the session's own stream, between the kernels:
+// no host round trip per iteration, the host only runs ahead of the device.  NCCL is resolved at
+// run time (dlopen of libnccl.so.2 — inside a torch process that is the copy torch already loaded),
+// so the library has no link-time dependency on it and single-GPU users never touch it.
+#include <dlfcn.h>
+
+namespace {
+typedef struct ncclComm *nccl_comm_t;
+struct nccl_uid { char internal[128]; };                                 // NCCL_UNIQUE_ID_BYTES
+enum { kNcclFloat32 = 7, kNcclFloat64 = 8 };                             // ncclDataType_t values (nccl.h)
+struct NcclApi {
+    int (*GetUniqueId)(nccl_uid *);
+    int (*CommInitRank)(nccl_comm_t *, int, nccl_uid, int);
+    int (*CommDestroy)(nccl_comm_t);
+    int (*Send)(const void *, size_t, int, int, nccl_comm_t, cudaStream_t);
+    int (*Recv)(void *, size_t, int, int, nccl_comm_t, cudaStream_t);
+    int (*AllGather)(const void *, void *, size_t, int, nccl_comm_t, cudaStream_t);
+    int (*GroupStart)();
+    int (*GroupEnd)();
+    const char *(*GetErrorString)(int);
+    bool ok = false;
+};
+NcclApi g_nccl;
+std::once_flag g_nccl_once;
+
+const NcclApi *nccl_api() {
+    std::call_once(g_nccl_once, [] {
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return;
+        NcclApi &a = g_nccl;
+#define J2P_SYM(field, name) *(void **)(&a.field) = dlsym(h, name)
+        J2P_SYM(GetUniqueId, "ncclGetUniqueId");
+        J2P_SYM(CommInitRank, "ncclCommInitRank");
+        J2P_SYM(CommDestroy, "ncclCommDestroy");
+        J2P_SYM(Send, "ncclSend");
+        J2P_SYM(Recv, "ncclRecv");
+        J2P_SYM(AllGather, "ncclAllGather");
+        J2P_SYM(GroupStart, "ncclGroupStart");
+        J2P_SYM(GroupEnd, "ncclGroupEnd");
+        J2P_SYM(GetErrorString, "ncclGetErrorString");
+#undef J2P_SYM
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.Send && a.Recv && a.AllGather && a.GroupStart && a.GroupEnd &&
+               a.GetErrorString;
+    });
+    return g_nccl.ok ? &g_nccl : nullptr;
+}
+}  // namespace
+
+struct j2p_comm {
+    nccl_comm_t comm = nullptr;
+    int nranks = 0, rank = 0, device = 0;
+    double *gathered = nullptr;                                          // [nranks][3] fp64, device
+};
+
+#define NK(call)                                                                                      \
+    do {                                                                                              \
+        int r_ = (call);                                                                              \
+        if (r_ != 0) return fail(J2P_ERR_CUDA, "%s failed: %s (%s:%d)", #call, api->GetErrorString(r_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" int j2p_comm_unique_id(void *out, size_t bytes) {
+    const NcclApi *api = nccl_api();
+    if (!api) return fail(J2P_ERR_NODEVICE, "libnccl.so.2 could not be loaded: %s", dlerror());
+    if (!out || bytes < sizeof(nccl_uid)) return fail(J2P_ERR_ARG, "the id buffer must hold %zu bytes", sizeof(nccl_uid));
+    NK(api->GetUniqueId((nccl_uid *)out));
+    return J2P_OK;
+}
+
+extern "C" int j2p_comm_create(j2p_comm **out, int device, int nranks, int rank, const void *id, size_t bytes) {
+    if (!out || !id || bytes < sizeof(nccl_uid) || nranks < 1 || rank < 0 || rank >= nranks) return fail(J2P_ERR_ARG, "bad argument");
+    const NcclApi *api = nccl_api();
+    if (!api) return fail(J2P_ERR_NODEVICE, "libnccl.so.2 could not be loaded: %s", dlerror());
+    CK(cudaSetDevice(device));
+    j2p_comm *c = new j2p_comm;
+    c->nranks = nranks;
+    c->rank = rank;
+    c->device = device;
+    nccl_uid uid;
+    memcpy(&uid, id, sizeof uid);
+    int r = api->CommInitRank(&c->comm, nranks, uid, rank);
+    if (r != 0) {
+        delete c;
+        return fail(J2P_ERR_CUDA, "ncclCommInitRank failed: %s", api->GetErrorString(r));
+    }
+    if (cudaMalloc(&c->gathered, sizeof(double) * 3 * (size_t)nranks) != cudaSuccess) {
+        api->CommDestroy(c->comm);
+        delete c;
+        return fail(J2P_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    *out = c;
+    return J2P_OK;
+}
+
+extern "C" void j2p_comm_destroy(j2p_comm *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    const NcclApi *api = nccl_api();
+    if (api && c->comm) api->CommDestroy(c->comm);
+    cudaFree(c->gathered);
+    delete c;
+}
+
+// the two border rows of the current iterate, all planes, both neighbours: one NCCL group
+static int exchange_halos_nccl(j2p_session *s, j2p_comm *c, const NcclApi *api) {
+    const FrameDev &F = s->F;
+    const size_t W = (size_t)F.W;
+    const bool up = F.t0 > 0 && c->rank > 0, down = F.t1 < F.H && c->rank + 1 < c->nranks;
+    if (!up && !down) return J2P_OK;
+    NK(api->GroupStart());
+    for (int k = 0; k < F.nc; k++) {
+        float *x = F.pl[k].x;
+        if (up) {
+            NK(api->Send(x + (size_t)F.t0 * W, 2 * W, kNcclFloat32, c->rank - 1, c->comm, s->stream));
+            NK(api->Recv(x + (size_t)(F.t0 - 2) * W, 2 * W, kNcclFloat32, c->rank - 1, c->comm, s->stream));
+        }
+        if (down) {
+            NK(api->Send(x + (size_t)(F.t1 - 2) * W, 2 * W, kNcclFloat32, c->rank + 1, c->comm, s->stream));
+            NK(api->Recv(x + (size_t)F.t1 * W, 2 * W, kNcclFloat32, c->rank + 1, c->comm, s->stream));
+        }
+    }
+    NK(api->GroupEnd());
+    return J2P_OK;
+}
+
+// `n` iterations of this rank's strip; collective over the communicator (every rank calls it with
+// the same n).  The first call after (re)arming the session also fills the halo rows of x_0 and
+// x_{-1}.  Everything is queued on the session stream; use j2p_session_sync / download to wait.
+extern "C" int j2p_session_iterate_strip(j2p_session *s, j2p_comm *c, unsigned n) {
+    if (!s || !c) return fail(J2P_ERR_ARG, "null argument");
+    const NcclApi *api = nccl_api();
+    if (!api) return fail(J2P_ERR_NODEVICE, "libnccl.so.2 could not be loaded");
+    if (c->device != s->device) return fail(J2P_ERR_ARG, "communicator and session live on different devices");
+    CK(cudaSetDevice(s->device));
+    for (int k = 0; k < s->F.nc; k++)
+        if (!s->uploaded[k]) return fail(J2P_ERR_ARG, "plane %d has not been uploaded", k);
+    FrameDev &F = s->F;
+    int rc;
+    if (s->next_iter == 0) {
+        if ((rc = exchange_halos_nccl(s, c, api)) != J2P_OK) return rc;
+        if ((rc = j2p_session_copy_halo_to_prev(s)) != J2P_OK) return rc;
+    }
+    for (unsigned i = 0; i < n; i++) {
+        const float tnext = (1 + sqrtf(1 + 4 * (s->t * s->t))) / 2;      // compute.c:431-432, :440
+        const float factor = (s->t - 1) / tnext;
+        s->t = tnext;
+        CK(launch_gradient(F, factor, s->stream));
+        NK(api->AllGather(F.sums, c->gathered, 3, kNcclFloat64, c->comm, s->stream));
+        CK(launch_fold_sums(c->gathered, c->nranks, F.nc, F.norms, s->stream));
+        CK(launch_project(F, factor, s->stream));
+        s->launches += 2 + (unsigned)F.nc;
+        for (int k = 0; k < F.nc; k++) {                                 // compute.c:438
+            float *tmp = F.pl[k].x;
+            F.pl[k].x = F.pl[k].xp;
+            F.pl[k].xp = tmp;
+        }
+        s->next_iter++;
+        if ((rc = exchange_halos_nccl(s, c, api)) != J2P_OK) return rc;
+    }
+    return J2P_OK;
+}

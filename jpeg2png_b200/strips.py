@@ -168,3 +168,28 @@ def solve_strips(backend, dist, rank, world, iterations, nchannel=3):
                 gathered.copy_(sums)
             backend.project(gathered, world)
             exchange_halos(backend, dist, rank, world, nchannel)
+
+
+def native_comm(backend, dist, rank, world):
+    """An NCCL communicator owned by libjpeg2png_b200.so for the native strip loop.  The 128-byte
+    NCCL id is made on rank 0 and handed round with torch.distributed (any backend)."""
+    import torch
+    lib = backend.lib
+    buf = (C.c_ubyte * 128)()
+    if rank == 0 and lib.j2p_comm_unique_id(buf, 128) != 0:
+        raise RuntimeError(lib.j2p_last_error().decode())
+    ids = [bytes(buf)]
+    if world > 1:
+        dist.broadcast_object_list(ids, src=0)
+    raw = (C.c_ubyte * 128).from_buffer_copy(ids[0])
+    comm = C.c_void_p()
+    if lib.j2p_comm_create(C.byref(comm), backend.device.index, world, rank, raw, 128) != 0:
+        raise RuntimeError(lib.j2p_last_error().decode())
+    return comm
+
+
+def solve_strips_native(backend, comm, iterations):
+    """`iterations` solver iterations of this rank's strip, both exchanges queued by the library on
+    the session stream through NCCL (j2p_session_iterate_strip).  Collective; asynchronous."""
+    if backend.lib.j2p_session_iterate_strip(backend.s, comm, iterations) != 0:
+        raise RuntimeError(backend.lib.j2p_last_error().decode())

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 CASE = dict(w=640, h=512, q=20, ss='4:2:0', weight=0.3, pw=[0.001] * 3, iters=25)
 
 
-def _worker(rank, world, init_file, out_dir):
+def _worker(rank, world, init_file, out_dir, native):
     import torch
     import torch.distributed as dist
     from jpeg2png_b200 import abi, strips, synth
@@ -25,16 +25,26 @@ def _worker(rank, world, init_file, out_dir):
         mcu = 8 * max(p.h_samp for p in img.planes)
         row0, rows = strips.plan_strips(img.frame_h, mcu, world)[rank]
         be = strips.ProductStrip(lib, img, CASE['weight'], CASE['pw'], CASE['iters'], row0, rows, rank)
-        strips.solve_strips(be, dist, rank, world, CASE['iters'])
+        if native:
+            # the library's own loop: NCCL all-gather + halo send/recv queued on the session stream,
+            # in two calls to cover the continuation path
+            comm = strips.native_comm(be, dist, rank, world)
+            strips.solve_strips_native(be, comm, 10)
+            strips.solve_strips_native(be, comm, CASE['iters'] - 10)
+        else:
+            strips.solve_strips(be, dist, rank, world, CASE['iters'])
         np.savez(os.path.join(out_dir, f'rank{rank}.npz'), rows=rows, **{f'p{c}': be.download(c) for c in range(3)})
+        if native:
+            lib.j2p_comm_destroy(comm)
         be.close()
         dist.barrier()
     finally:
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize('native', [False, True], ids=['torchdist', 'native'])
 @pytest.mark.parametrize('world', [2, 4, 8])
-def test_strips_match_single_gpu(world, tmp_path):
+def test_strips_match_single_gpu(world, native, tmp_path):
     import torch
     import torch.multiprocessing as mp
     from jpeg2png_b200 import synth
@@ -42,7 +52,7 @@ def test_strips_match_single_gpu(world, tmp_path):
     if torch.cuda.device_count() < world:
         pytest.skip(f'needs {world} GPUs')
     init_file = tempfile.mktemp(dir=str(tmp_path))
-    mp.spawn(_worker, args=(world, init_file, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, init_file, str(tmp_path), native), nprocs=world, join=True)
     img = synth.synth_coefs(CASE['w'], CASE['h'], CASE['q'], CASE['ss'], seed=777)
     want = H.run_compute('product', img, [0, 1, 2], CASE['weight'], CASE['pw'], CASE['iters'])
     parts = [np.load(os.path.join(str(tmp_path), f'rank{r}.npz')) for r in range(world)]

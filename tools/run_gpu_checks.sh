@@ -1,6 +1,13 @@
-export J2P_EXPECT_GPU=1
+#!/bin/bash
+# multi-GPU strip checks: parity tests, then strong scaling of one 8K frame (N from $1...)
 mkdir -p gpurun_out
-python tools/quick_time.py build_ab/lib_base.so build_ab/lib_cur.so build_ab/lib_g4.so build_ab/lib_t5.so build_ab/lib_t6.so 2>&1 | grep lib_
-J2P_TRACE=1 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_trace.json 2> gpurun_out/bench_trace.err
-grep -E "trace" gpurun_out/bench_trace.err | tail -14
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+NG=$(nvidia-smi -L | wc -l)
+echo "GPUs: $NG" > gpurun_out/strips.log
+timeout 600 python -m pytest tests/test_gpu_strips.py -m gpu -q -x ${PYTEST_K:+-k "$PYTEST_K"} >> gpurun_out/strips.log 2>&1
+echo "pytest exit $?" >> gpurun_out/strips.log
+for n in "$@"; do
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533 \
+      tools/strip_bench.py >> gpurun_out/strips.log 2> gpurun_out/strips_err_$n.log
+  echo "strip_bench N=$n exit $?" >> gpurun_out/strips.log
+done
+grep -v "^$" gpurun_out/strips.log | tail -40
