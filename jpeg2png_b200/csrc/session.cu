@@ -101,9 +101,15 @@ static PinnedPool g_pinned;
 static void par_memcpy(void *dst, const void *src, size_t bytes) {
     const size_t piece = 1u << 20;
     const long n = (long)((bytes + piece - 1) / piece);
-    // four threads saturate the copy; a team as wide as the machine (128 hardware threads on the GPU
-    // boxes) spends two orders of magnitude longer waking up than copying (profiles/r01_notes.md)
-#pragma omp parallel for schedule(static) num_threads(4) if (n > 2)
+    // a small team: one as wide as the machine (128 hardware threads on the GPU boxes) spends two
+    // orders of magnitude longer waking up than copying (profiles/r01_notes.md).  J2P_COPY_THREADS
+    // overrides the default for tuning.
+    static const int nthreads = [] {
+        const char *e = getenv("J2P_COPY_THREADS");
+        const int v = e ? atoi(e) : 0;
+        return v > 0 && v <= 64 ? v : 4;
+    }();
+#pragma omp parallel for schedule(static) num_threads(nthreads) if (n > 2)
     for (long i = 0; i < n; i++) {
         const size_t off = (size_t)i * piece;
         memcpy((char *)dst + off, (const char *)src + off, bytes - off < piece ? bytes - off : piece);

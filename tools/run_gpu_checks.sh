@@ -1,13 +1,18 @@
 #!/bin/bash
-# multi-GPU strip checks: parity tests, then strong scaling of one 8K frame (N from $1...)
+# round-end evidence run on one GPU: staging-thread A/B, GPU tests, bench + ncu captures
 mkdir -p gpurun_out
-NG=$(nvidia-smi -L | wc -l)
-echo "GPUs: $NG" > gpurun_out/strips.log
-timeout 600 python -m pytest tests/test_gpu_strips.py -m gpu -q -x ${PYTEST_K:+-k "$PYTEST_K"} >> gpurun_out/strips.log 2>&1
-echo "pytest exit $?" >> gpurun_out/strips.log
-for n in "$@"; do
-  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533 \
-      tools/strip_bench.py >> gpurun_out/strips.log 2> gpurun_out/strips_err_$n.log
-  echo "strip_bench N=$n exit $?" >> gpurun_out/strips.log
+for t in 4 8 16; do
+  echo "== J2P_COPY_THREADS=$t" >> gpurun_out/copy_ab.log
+  J2P_COPY_THREADS=$t timeout 200 python tools/e2e_trace.py 2>&1 | grep -v "^$" | tail -12 >> gpurun_out/copy_ab.log
 done
-grep -v "^$" gpurun_out/strips.log | tail -40
+tail -45 gpurun_out/copy_ab.log
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1
+tail -3 gpurun_out/pytest_gpu.log
+TAG=r01b
+export J2P_EXPECT_GPU=1
+python bench.py --steps 5 --warmup 3 > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err
+tail -c 2500 gpurun_out/bench_${TAG}.json
+tail -5 gpurun_out/bench_${TAG}.err
+ncu --metrics gpu__time_duration.sum --clock-control none -s 12 -c 32 --csv --log-file gpurun_out/launches_${TAG}.csv python tools/prof_driver.py > gpurun_out/ncu_list_${TAG}.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_gradient -s 4 -c 1 -o gpurun_out/prof_gradient_${TAG} -f python tools/prof_driver.py > gpurun_out/ncu_grad_${TAG}.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_project -s 12 -c 1 -o gpurun_out/prof_project_${TAG} -f python tools/prof_driver.py > gpurun_out/ncu_proj_${TAG}.log 2>&1
