@@ -45,16 +45,64 @@ namespace j2p {
 // is set to 0, which makes every quotient of that pixel exactly 0.
 // ------------------------------------------------------------------------------------------
 constexpr int GM_WARPS = 4, GM_NT = GM_WARPS * 32, GM_USE = 60;
-#ifndef J2P_FAST_ROOTS
-#define J2P_FAST_ROOTS 1        // sqrt_core / rcp_core (numerics.cuh; exhaustively equal to sqrt.rn / rcp.rn, profiles/r01_rootcheck.txt); 0 = IEEE intrinsics
-#endif
 #ifndef J2P_GRAD_MIN_CTAS
 #define J2P_GRAD_MIN_CTAS 3     // resident CTAs per SM the register allocation is bounded for (4 spills: measured slower)
 #endif
 
+// IEEE fallbacks of the two quotient stages, for rows the guards reject (numerics.cuh).  Out of line
+// and fed through local memory on purpose: they run once in millions of rows, and kept inline they
+// cost the hot path register copies at every row.
+template <int NC>
+struct TvSlow {
+    float gx[NC][2], gy[NC][2];     // in: forward differences of the source row
+    float q[3][NC][2];              // out: self / right / below quotients (compute.c:98-103)
+    float n[2];                     // out: the norms (for the objective log)
+};
+template <int NC>
+__device__ __noinline__ void tv_slow(TvSlow<NC> *io, float a1, bool src_in) {
+    for (int k = 0; k < 2; k++) {
+        float ssq = 0.f;
+        for (int c = 0; c < NC; c++) ssq = fadd(fadd(ssq, fsq(io->gx[c][k])), fsq(io->gy[c][k]));   // compute.c:84-89
+        const float n = fsqrt(ssq);
+        const bool live = src_in && n != 0.f;                                                       // compute.c:97
+        io->n[k] = n;
+        for (int c = 0; c < NC; c++) {
+            const float gx = io->gx[c][k], gy = io->gy[c][k];
+            io->q[0][c][k] = live ? fdiv(fmul(a1, -fadd(gx, gy)), n) : 0.f;
+            io->q[1][c][k] = live ? fdiv(fmul(a1, gx), n) : 0.f;
+            io->q[2][c][k] = live ? fdiv(fmul(a1, gy), n) : 0.f;
+        }
+    }
+}
+template <int NC>
+struct TgvSlow {
+    float gxx[NC][2], gyy[NC][2], sym[NC][2];   // in: second differences of the source row
+    float q[4][NC][2];                          // out: a2 * (self / left-right / up-down / diagonal quotients) (compute.c:165-182)
+    float n[2];
+};
+template <int NC>
+__device__ __noinline__ void tgv_slow(TgvSlow<NC> *io, float a2, bool src_in) {
+    for (int k = 0; k < 2; k++) {
+        float ssq = 0.f;
+        for (int c = 0; c < NC; c++)
+            ssq = fadd(ssq, fadd(fadd(fsq(io->gxx[c][k]), fmul(2.f, fsq(io->sym[c][k]))), fsq(io->gyy[c][k])));   // compute.c:148-152
+        const float n = fsqrt(ssq);
+        const bool live = src_in && n != 0.f;                                                       // compute.c:158
+        io->n[k] = n;
+        for (int c = 0; c < NC; c++) {
+            const float gxx = io->gxx[c][k], gyy = io->gyy[c][k], sym = io->sym[c][k];
+            const float self = -fadd(fadd(fmul(2.f, gxx), fmul(2.f, sym)), fmul(2.f, gyy));
+            io->q[0][c][k] = live ? fmul(a2, fdiv(self, n)) : 0.f;
+            io->q[1][c][k] = live ? fmul(a2, fdiv(fadd(sym, gxx), n)) : 0.f;
+            io->q[2][c][k] = live ? fmul(a2, fdiv(fadd(gyy, sym), n)) : 0.f;
+            io->q[3][c][k] = live ? fmul(a2, fdiv(-sym, n)) : 0.f;
+        }
+    }
+}
+
 // LOG: additionally sum the objective terms the reference logs (compute.c:91,155: tv += alpha*norm
 // per pixel, fp64) — only instantiated for sessions with logging enabled (-c csv).
-template <int NC, bool LOG>
+template <int NC, bool LOG, bool TGV>
 __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient(const __grid_constant__ FrameDev F, const float factor, const int band_rows) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int W = F.W, H = F.H;
@@ -66,8 +114,7 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient(const __g
     const bool pair_in = px0 >= 0 && px0 < W;
     const bool is_target = pair_in && lane >= 1 && lane <= 30;
     const bool has_l0 = px0 > 0, has_r1 = px0 + 1 < W - 1;   // k=1 always has a left neighbour, k=0 a right one
-    const float a1 = F.a1, a2 = F.a2;
-    const bool use_tgv = F.use_tgv != 0;
+    const float a1 = F.a1, a2 = F.a2, a2m2 = fmul(-2.f, F.a2);
 
     double acc[NC];
     double tv_acc = 0., tv2_acc = 0.;
@@ -129,231 +176,243 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient(const __g
         }
     };
 
-    if (X0 < W) {
-        issue_row_loads(yb - 2);
-        for (int i = yb - 2; i <= ye + 1; i++) {
-            // ---- FISTA point of row i (compute.c:436) from the loads issued one step ago -------
-            float yN[NC][2];
+    // Warps whose strip starts beyond the frame (only in the last CTA column of odd widths) run the
+    // same loop on clamped loads and store nothing: control flow then depends on block indices and
+    // kernel parameters only, so the compiler knows every shuffle below is executed convergently.
+    bool okP1 = true, okP2 = true;      // magnitude guard of rows i-1 and i-2 (warp-uniform)
+    issue_row_loads(yb - 2);
+    for (int i = yb - 2; i <= ye + 1; i++) {
+        // ---- FISTA point of row i (compute.c:436) from the loads issued one step ago -----------
+        float yN[NC][2];
+        unsigned ykey = 0xffffffffu;
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            yN[c][0] = fadd(ldx[c].x, fmul(factor, fsub(ldx[c].x, ldp[c].x)));
+            yN[c][1] = fadd(ldx[c].y, fmul(factor, fsub(ldx[c].y, ldp[c].y)));
+            ykey = min(ykey, min(qdiv_key(yN[c][0]), qdiv_key(yN[c][1])));
+        }
+        // one guard per VALUE instead of one per numerator (numerics.cuh, "row guard")
+        const bool ok0 = !__any_sync(0xffffffffu, ykey < QDIV_YKEY_MIN);
+        float gpv[NC][2];
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            gpv[c][0] = (pgp_ok >> (c * 2)) & 1u ? pgp[c][0] : 0.f;
+            gpv[c][1] = (pgp_ok >> (c * 2)) & 2u ? pgp[c][1] : 0.f;
+        }
+        issue_row_loads(i + 1);                                 // clamped: the one row too many at the end is harmless
+        if (i >= yb && i < ye) issue_gp_loads();               // consumed next step, where the target row is s = i
+
+        {
+            const int s = i - 1;
+            const bool src_in = pair_in && s >= 0 && s < H;
+            if (s >= s_last) {                                  // no row below in the frame: gy := 0 (compute.c:81)
+#pragma unroll
+                for (int c = 0; c < NC; c++) { yN[c][0] = yP[c][0]; yN[c][1] = yP[c][1]; }
+            }
+
+            // ---- source row s: TV (compute.c:79-105) -------------------------------------------
+            float gx0[NC][2], gy0[NC][2], tvs0[NC][2], tvr0[NC][2], tvb0[NC][2];
+            float n1[2] = {0.f, 0.f};
 #pragma unroll
             for (int c = 0; c < NC; c++) {
-                yN[c][0] = fadd(ldx[c].x, fmul(factor, fsub(ldx[c].x, ldp[c].x)));
-                yN[c][1] = fadd(ldx[c].y, fmul(factor, fsub(ldx[c].y, ldp[c].y)));
-            }
-            float gpv[NC][2];
-#pragma unroll
-            for (int c = 0; c < NC; c++) {
-                gpv[c][0] = (pgp_ok >> (c * 2)) & 1u ? pgp[c][0] : 0.f;
-                gpv[c][1] = (pgp_ok >> (c * 2)) & 2u ? pgp[c][1] : 0.f;
-            }
-            if (i < ye + 1) issue_row_loads(i + 1);
-            if (i >= yb && i < ye) issue_gp_loads();               // consumed next step, where the target row is s = i
-
-            if (i >= yb - 1) {
-                const int s = i - 1;
-                const bool src_in = pair_in && s >= 0 && s < H;
-                if (s >= s_last) {                                  // no row below in the frame: gy := 0 (compute.c:81)
-#pragma unroll
-                    for (int c = 0; c < NC; c++) { yN[c][0] = yP[c][0]; yN[c][1] = yP[c][1]; }
-                }
-
-                // ---- source row s: TV (compute.c:79-105) ---------------------------------------
-                float gx0[NC][2], gy0[NC][2], tvs0[NC][2], tvr0[NC][2], tvb0[NC][2];
-                float n1[2] = {0.f, 0.f};
-#pragma unroll
-                for (int c = 0; c < NC; c++) {
-                    float yr1 = __shfl_down_sync(0xffffffffu, yP[c][0], 1);
-                    yr1 = has_r1 ? yr1 : yP[c][1];                  // no right neighbour: gx := 0 (compute.c:79)
-                    gx0[c][0] = fsub(yP[c][1], yP[c][0]);
-                    gx0[c][1] = fsub(yr1, yP[c][1]);
-#pragma unroll
-                    for (int k = 0; k < 2; k++) {
-                        gy0[c][k] = fsub(yN[c][k], yP[c][k]);
-                        n1[k] = fadd(n1[k], fsq(gx0[c][k]));
-                        n1[k] = fadd(n1[k], fsq(gy0[c][k]));
-                    }
-                }
+                float yr1 = __shfl_down_sync(0xffffffffu, yP[c][0], 1);
+                yr1 = has_r1 ? yr1 : yP[c][1];                  // no right neighbour: gx := 0 (compute.c:79)
+                gx0[c][0] = fsub(yP[c][1], yP[c][0]);
+                gx0[c][1] = fsub(yr1, yP[c][1]);
 #pragma unroll
                 for (int k = 0; k < 2; k++) {
-                    const float ssq = n1[k];
-                    float n, y;
-                    bool live, guard_ok;
-                    if (!LOG && J2P_FAST_ROOTS) {                                 // branch-free roots inside the guarded range (numerics.cuh)
-                        guard_ok = root_arg_ok(ssq);
-                        live = src_in && ssq != 0.f;                              // sqrtf(x) != 0  <=>  x != 0   (compute.c:97)
-                        n = guard_ok ? sqrt_core(ssq) : 1.f;
-                        y = (live && guard_ok) ? rcp_core(n) : 0.f;
-                    } else {
-                        n = fsqrt(ssq);
-                        live = src_in && n != 0.f;                                // compute.c:97
-                        y = live ? __frcp_rn(n) : 0.f;
-                        guard_ok = qdiv_divisor_ok(n);
-                    }
-                    if (LOG && is_target && s >= yb && s < ye) tv_acc = __dadd_rn(tv_acc, (double)fmul(a1, n));   // compute.c:91
-                    unsigned key = 0xffffffffu;
-                    float num[NC][3];
-#pragma unroll
-                    for (int c = 0; c < NC; c++) {
-                        num[c][0] = fmul(a1, -fadd(gx0[c][k], gy0[c][k]));                         // compute.c:98
-                        num[c][1] = fmul(a1, gx0[c][k]);                                           // compute.c:100
-                        num[c][2] = fmul(a1, gy0[c][k]);                                           // compute.c:103
-                        key = min(key, min(qdiv_key(num[c][0]), min(qdiv_key(num[c][1]), qdiv_key(num[c][2]))));
-                        tvs0[c][k] = qdiv_core(num[c][0], n, y);
-                        tvr0[c][k] = qdiv_core(num[c][1], n, y);
-                        tvb0[c][k] = qdiv_core(num[c][2], n, y);
-                    }
-                    if (live && !(key >= QDIV_KEY_MIN && guard_ok)) {              // outside the proven range: IEEE square root and division
-                        n = fsqrt(ssq);
-#pragma unroll
-                        for (int c = 0; c < NC; c++) {
-                            tvs0[c][k] = fdiv(num[c][0], n);
-                            tvr0[c][k] = fdiv(num[c][1], n);
-                            tvb0[c][k] = fdiv(num[c][2], n);
-                        }
-                    }
+                    gy0[c][k] = fsub(yN[c][k], yP[c][k]);
+                    n1[k] = fadd(n1[k], fsq(gx0[c][k]));
+                    n1[k] = fadd(n1[k], fsq(gy0[c][k]));
                 }
-
-                // ---- source row s: second-order TGV (compute.c:136-183) ------------------------
-                float t2s0[NC][2], lr0[NC][2], ud0[NC][2], dg0[NC][2];
-                if (use_tgv && i >= yb) {
-                    if (s <= s_first) {                             // no row above in the frame: gxy, gyy := 0 (compute.c:141-143)
-#pragma unroll
-                        for (int c = 0; c < NC; c++)
-#pragma unroll
-                            for (int k = 0; k < 2; k++) { gxP[c][k] = gx0[c][k]; gyP[c][k] = gy0[c][k]; }
-                    }
-                    float gxx[NC][2], gyy[NC][2], sym[NC][2];
-                    float n2[2] = {0.f, 0.f};
-#pragma unroll
-                    for (int c = 0; c < NC; c++) {
-                        float gxl = __shfl_up_sync(0xffffffffu, gx0[c][1], 1);
-                        float gyl = __shfl_up_sync(0xffffffffu, gy0[c][1], 1);
-                        gxl = has_l0 ? gxl : gx0[c][0];             // no left neighbour: gxx, gyx := 0 (compute.c:137-139)
-                        gyl = has_l0 ? gyl : gy0[c][0];
-#pragma unroll
-                        for (int k = 0; k < 2; k++) {
-                            const float gx_l = k ? gx0[c][0] : gxl, gy_l = k ? gy0[c][0] : gyl;
-                            gxx[c][k] = fsub(gx0[c][k], gx_l);
-                            const float gyx = fsub(gy0[c][k], gy_l);
-                            const float gxy = fsub(gx0[c][k], gxP[c][k]);
-                            gyy[c][k] = fsub(gy0[c][k], gyP[c][k]);
-                            sym[c][k] = fmul(fadd(gxy, gyx), 0.5f);               // (gxy+gyx)/2., exact either way
-                            n2[k] = fadd(n2[k], fadd(fadd(fsq(gxx[c][k]), fmul(2.f, fsq(sym[c][k]))), fsq(gyy[c][k])));
-                        }
-                    }
+            }
+            {
+                const bool g0 = root_arg_ok(n1[0]), g1 = root_arg_ok(n1[1]);
+                const bool l0 = src_in && n1[0] != 0.f, l1 = src_in && n1[1] != 0.f;   // sqrtf(x) != 0  <=>  x != 0   (compute.c:97)
+                const bool fast = ok0 && okP1 && !__any_sync(0xffffffffu, (l0 && !g0) || (l1 && !g1));
+                if (__builtin_expect(fast, true)) {
 #pragma unroll
                     for (int k = 0; k < 2; k++) {
-                        const float ssq = n2[k];
-                        float n, y;
-                        bool live, guard_ok;
-                        if (!LOG && J2P_FAST_ROOTS) {
-                            guard_ok = root_arg_ok(ssq);
-                            live = src_in && ssq != 0.f;                          // compute.c:158
-                            n = guard_ok ? sqrt_core(ssq) : 1.f;
-                            y = (live && guard_ok) ? rcp_core(n) : 0.f;
-                        } else {
-                            n = fsqrt(ssq);
-                            live = src_in && n != 0.f;                            // compute.c:158
-                            y = live ? __frcp_rn(n) : 0.f;
-                            guard_ok = qdiv_divisor_ok(n);
-                        }
-                        if (LOG && is_target && s >= yb && s < ye) tv2_acc = __dadd_rn(tv2_acc, (double)fmul(a2, n));   // compute.c:155
-                        unsigned key = 0xffffffffu;
-                        float num[NC][4];
+                        const bool g = k ? g1 : g0, live = k ? l1 : l0;
+                        const float r = sqrt_core(n1[k]);
+                        const float n = g ? r : 1.f;
+                        const float yr = rcp_core(n);
+                        const float y = (live && g) ? yr : 0.f;             // dead source: every quotient is exactly 0
+                        if (LOG && is_target && s >= yb && s < ye) tv_acc = __dadd_rn(tv_acc, (double)fmul(a1, g ? n : 0.f));   // compute.c:91
 #pragma unroll
                         for (int c = 0; c < NC; c++) {
-                            num[c][0] = -fadd(fadd(fmul(2.f, gxx[c][k]), fmul(2.f, sym[c][k])), fmul(2.f, gyy[c][k]));
-                            num[c][1] = fadd(sym[c][k], gxx[c][k]);
-                            num[c][2] = fadd(gyy[c][k], sym[c][k]);
-                            num[c][3] = -sym[c][k];
-                            key = min(min(key, qdiv_key(num[c][0])), min(qdiv_key(num[c][1]), min(qdiv_key(num[c][2]), qdiv_key(num[c][3]))));
-                            t2s0[c][k] = qdiv_core(num[c][0], n, y);
-                            lr0[c][k] = qdiv_core(num[c][1], n, y);
-                            ud0[c][k] = qdiv_core(num[c][2], n, y);
-                            dg0[c][k] = qdiv_core(num[c][3], n, y);
-                        }
-                        if (live && !(key >= QDIV_KEY_MIN && guard_ok)) {
-                            n = fsqrt(ssq);
-#pragma unroll
-                            for (int c = 0; c < NC; c++) {
-                                t2s0[c][k] = fdiv(num[c][0], n);
-                                lr0[c][k] = fdiv(num[c][1], n);
-                                ud0[c][k] = fdiv(num[c][2], n);
-                                dg0[c][k] = fdiv(num[c][3], n);
-                            }
-                        }
-#pragma unroll
-                        for (int c = 0; c < NC; c++) {
-                            t2s0[c][k] = fmul(a2, t2s0[c][k]);                    // compute.c:165
-                            lr0[c][k] = fmul(a2, lr0[c][k]);                      // compute.c:167,170
-                            ud0[c][k] = fmul(a2, ud0[c][k]);                      // compute.c:173,176
-                            dg0[c][k] = fmul(a2, dg0[c][k]);                      // compute.c:179,182
+                            tvs0[c][k] = qdiv_core(fmul(a1, -fadd(gx0[c][k], gy0[c][k])), n, y);   // compute.c:98
+                            tvr0[c][k] = qdiv_core(fmul(a1, gx0[c][k]), n, y);                      // compute.c:100
+                            tvb0[c][k] = qdiv_core(fmul(a1, gy0[c][k]), n, y);                      // compute.c:103
                         }
                     }
-                } else {
+                } else {                                                    // outside the proven range: IEEE square root and division
+                    TvSlow<NC> io;
 #pragma unroll
                     for (int c = 0; c < NC; c++)
 #pragma unroll
-                        for (int k = 0; k < 2; k++) t2s0[c][k] = lr0[c][k] = ud0[c][k] = dg0[c][k] = 0.f;
-                }
-
-                // ---- target row s-1: last two addends, store, sum of squares -------------------
-                if (i >= yb + 2) {
-                    const size_t gi = (size_t)(s - 1) * W + (is_target ? px0 : 0);
+                        for (int k = 0; k < 2; k++) { io.gx[c][k] = gx0[c][k]; io.gy[c][k] = gy0[c][k]; }
+                    tv_slow<NC>(&io, a1, src_in);
 #pragma unroll
-                    for (int c = 0; c < NC; c++) {
-                        float o0 = ogp[c][0], o1 = ogp[c][1];
-                        if (use_tgv) {
-                            const float dgl = __shfl_up_sync(0xffffffffu, dg0[c][1], 1);
-                            o0 = fadd(fadd(o0, dgl), ud0[c][0]);                  // below-left, below
-                            o1 = fadd(fadd(o1, dg0[c][0]), ud0[c][1]);
-                        }
-                        if (is_target) {
-                            *reinterpret_cast<float2 *>(F.pl[c].g + gi) = make_float2(o0, o1);
-                            acc[c] = __dadd_rn(acc[c], (double)fsq(o0));          // compute.c:203
-                            acc[c] = __dadd_rn(acc[c], (double)fsq(o1));
-                        }
+                    for (int c = 0; c < NC; c++)
+#pragma unroll
+                        for (int k = 0; k < 2; k++) { tvs0[c][k] = io.q[0][c][k]; tvr0[c][k] = io.q[1][c][k]; tvb0[c][k] = io.q[2][c][k]; }
+                    if (LOG && is_target && s >= yb && s < ye) tv_acc = __dadd_rn(__dadd_rn(tv_acc, (double)fmul(a1, io.n[0])), (double)fmul(a1, io.n[1]));
+                }
+            }
+
+            // ---- target row s: addends 1..6.  The contributions saved from the row above are consumed
+            // here, before this row's TGV stage produces their successors, so each saved value and its
+            // successor can share a register (no copies at the end of the step).
+            float oA[NC][2];
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                const float p0 = fadd(0.f, gpv[c][0]), p1 = fadd(0.f, gpv[c][1]);               // compute.c:62 onto a zeroed gradient
+                const float tvr_l = __shfl_up_sync(0xffffffffu, tvr0[c][1], 1);
+                float o0 = fadd(fadd(fadd(p0, sv_tvb[c][0]), tvr_l), tvs0[c][0]);              // TV: above, left, self
+                float o1 = fadd(fadd(fadd(p1, sv_tvb[c][1]), tvr0[c][0]), tvs0[c][1]);
+                if (TGV) {
+                    const float dg_r = __shfl_down_sync(0xffffffffu, sv_dg[c][0], 1);
+                    o0 = fadd(fadd(o0, sv_ud[c][0]), sv_dg[c][1]);                              // TGV: above, above-right
+                    o1 = fadd(fadd(o1, sv_ud[c][1]), dg_r);
+                }
+                oA[c][0] = o0;
+                oA[c][1] = o1;
+                sv_tvb[c][0] = tvb0[c][0];
+                sv_tvb[c][1] = tvb0[c][1];
+            }
+
+            // ---- source row s: second-order TGV (compute.c:136-183) ----------------------------
+            float t2s0[NC][2], lr0[NC][2], ud0[NC][2], dg0[NC][2];
+            if (TGV) {
+                if (s <= s_first) {                             // no row above in the frame: gxy, gyy := 0 (compute.c:141-143)
+#pragma unroll
+                    for (int c = 0; c < NC; c++)
+#pragma unroll
+                        for (int k = 0; k < 2; k++) { gxP[c][k] = gx0[c][k]; gyP[c][k] = gy0[c][k]; }
+                }
+                float gxx[NC][2], gyy[NC][2], sym[NC][2];
+                float n2[2] = {0.f, 0.f};
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    float gxl = __shfl_up_sync(0xffffffffu, gx0[c][1], 1);
+                    float gyl = __shfl_up_sync(0xffffffffu, gy0[c][1], 1);
+                    gxl = has_l0 ? gxl : gx0[c][0];             // no left neighbour: gxx, gyx := 0 (compute.c:137-139)
+                    gyl = has_l0 ? gyl : gy0[c][0];
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        const float gx_l = k ? gx0[c][0] : gxl, gy_l = k ? gy0[c][0] : gyl;
+                        gxx[c][k] = fsub(gx0[c][k], gx_l);
+                        const float gyx = fsub(gy0[c][k], gy_l);
+                        const float gxy = fsub(gx0[c][k], gxP[c][k]);
+                        gyy[c][k] = fsub(gy0[c][k], gyP[c][k]);
+                        const float u = fadd(gxy, gyx);
+                        sym[c][k] = fmul(u, 0.5f);                             // (gxy+gyx)/2., exact either way
+                        // 2*sym^2 as u*sym: 2*RN((u/2)^2) == RN(u*(u/2)) (power-of-two scalings commute with
+                        // rounding while nothing underflows; rows where that is not guaranteed are flagged
+                        // by the row guard and recompute n2 in the reference's form below)
+                        n2[k] = fadd(n2[k], fadd(fadd(fsq(gxx[c][k]), fmul(u, sym[c][k])), fsq(gyy[c][k])));
                     }
                 }
-
-                // ---- target row s: first nine addends ------------------------------------------
-                if (s >= yb && s < ye) {
+                const bool g0 = root_arg_ok(n2[0]), g1 = root_arg_ok(n2[1]);
+                const bool l0 = src_in && n2[0] != 0.f, l1 = src_in && n2[1] != 0.f;   // compute.c:158
+                const bool fast = ok0 && okP1 && okP2 && !__any_sync(0xffffffffu, (l0 && !g0) || (l1 && !g1));
+                if (__builtin_expect(fast, true)) {
 #pragma unroll
-                    for (int c = 0; c < NC; c++) {
-                        const float p0 = fadd(0.f, gpv[c][0]), p1 = fadd(0.f, gpv[c][1]);           // compute.c:62 onto a zeroed gradient
-                        const float tvr_l = __shfl_up_sync(0xffffffffu, tvr0[c][1], 1);
-                        float o0 = fadd(fadd(fadd(p0, sv_tvb[c][0]), tvr_l), tvs0[c][0]);          // above, left, self
-                        float o1 = fadd(fadd(fadd(p1, sv_tvb[c][1]), tvr0[c][0]), tvs0[c][1]);
-                        if (use_tgv) {
-                            const float dg_r = __shfl_down_sync(0xffffffffu, sv_dg[c][0], 1);
-                            const float lr_l = __shfl_up_sync(0xffffffffu, lr0[c][1], 1);
-                            const float lr_r = __shfl_down_sync(0xffffffffu, lr0[c][0], 1);
-                            // above, above-right, left, self, right
-                            o0 = fadd(fadd(fadd(fadd(fadd(o0, sv_ud[c][0]), sv_dg[c][1]), lr_l), t2s0[c][0]), lr0[c][1]);
-                            o1 = fadd(fadd(fadd(fadd(fadd(o1, sv_ud[c][1]), dg_r), lr0[c][0]), t2s0[c][1]), lr_r);
+                    for (int k = 0; k < 2; k++) {
+                        const bool g = k ? g1 : g0, live = k ? l1 : l0;
+                        const float r = sqrt_core(n2[k]);
+                        const float n = g ? r : 1.f;
+                        const float yr = rcp_core(n);
+                        const float y = (live && g) ? yr : 0.f;
+                        if (LOG && is_target && s >= yb && s < ye) tv2_acc = __dadd_rn(tv2_acc, (double)fmul(a2, g ? n : 0.f));   // compute.c:155
+#pragma unroll
+                        for (int c = 0; c < NC; c++) {
+                            // compute.c:165: a2 * (-(2gxx + 2s + 2gyy) / n) == (-2 a2) * (((s + gxx) + gyy) / n), again
+                            // because doubling commutes with every rounding involved (no overflow in this range)
+                            const float sx = fadd(sym[c][k], gxx[c][k]);
+                            t2s0[c][k] = fmul(a2m2, qdiv_core(fadd(sx, gyy[c][k]), n, y));
+                            lr0[c][k] = fmul(a2, qdiv_core(sx, n, y));                                      // compute.c:167,170
+                            ud0[c][k] = fmul(a2, qdiv_core(fadd(gyy[c][k], sym[c][k]), n, y));              // compute.c:173,176
+                            dg0[c][k] = fmul(a2, qdiv_core(-sym[c][k], n, y));                              // compute.c:179,182
                         }
-                        ogp[c][0] = o0;
-                        ogp[c][1] = o1;
                     }
+                } else {
+                    TgvSlow<NC> io;
+#pragma unroll
+                    for (int c = 0; c < NC; c++)
+#pragma unroll
+                        for (int k = 0; k < 2; k++) { io.gxx[c][k] = gxx[c][k]; io.gyy[c][k] = gyy[c][k]; io.sym[c][k] = sym[c][k]; }
+                    tgv_slow<NC>(&io, a2, src_in);
+#pragma unroll
+                    for (int c = 0; c < NC; c++)
+#pragma unroll
+                        for (int k = 0; k < 2; k++) { t2s0[c][k] = io.q[0][c][k]; lr0[c][k] = io.q[1][c][k]; ud0[c][k] = io.q[2][c][k]; dg0[c][k] = io.q[3][c][k]; }
+                    if (LOG && is_target && s >= yb && s < ye) tv2_acc = __dadd_rn(__dadd_rn(tv2_acc, (double)fmul(a2, io.n[0])), (double)fmul(a2, io.n[1]));
                 }
-
-                // ---- rotate ----------------------------------------------------------------------
+            } else {
 #pragma unroll
                 for (int c = 0; c < NC; c++)
 #pragma unroll
-                    for (int k = 0; k < 2; k++) {
-                        sv_tvb[c][k] = tvb0[c][k];
-                        sv_ud[c][k] = ud0[c][k];
-                        sv_dg[c][k] = dg0[c][k];
-                        gxP[c][k] = gx0[c][k];
-                        gyP[c][k] = gy0[c][k];
-                    }
+                    for (int k = 0; k < 2; k++) t2s0[c][k] = lr0[c][k] = ud0[c][k] = dg0[c][k] = 0.f;
             }
+
+            // ---- target row s-1: last two addends, store, sum of squares -----------------------
+            if (i >= yb + 2) {
+                float o[NC][2];
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    o[c][0] = ogp[c][0];
+                    o[c][1] = ogp[c][1];
+                    if (TGV) {
+                        const float dgl = __shfl_up_sync(0xffffffffu, dg0[c][1], 1);
+                        o[c][0] = fadd(fadd(o[c][0], dgl), ud0[c][0]);        // below-left, below
+                        o[c][1] = fadd(fadd(o[c][1], dg0[c][0]), ud0[c][1]);
+                    }
+                }
+                if (is_target) {
+                    const size_t gi = (size_t)(s - 1) * W + px0;
+#pragma unroll
+                    for (int c = 0; c < NC; c++) {
+                        *reinterpret_cast<float2 *>(F.pl[c].g + gi) = make_float2(o[c][0], o[c][1]);
+                        acc[c] = __dadd_rn(acc[c], (double)fsq(o[c][0]));     // compute.c:203
+                        acc[c] = __dadd_rn(acc[c], (double)fsq(o[c][1]));
+                    }
+                }
+            }
+
+            // ---- target row s: addends 7..9 (left, self, right of this row's TGV quotients) ------
 #pragma unroll
             for (int c = 0; c < NC; c++) {
-                yP[c][0] = yN[c][0];
-                yP[c][1] = yN[c][1];
+                float o0 = oA[c][0], o1 = oA[c][1];
+                if (TGV) {
+                    const float lr_l = __shfl_up_sync(0xffffffffu, lr0[c][1], 1);
+                    const float lr_r = __shfl_down_sync(0xffffffffu, lr0[c][0], 1);
+                    o0 = fadd(fadd(fadd(o0, lr_l), t2s0[c][0]), lr0[c][1]);
+                    o1 = fadd(fadd(fadd(o1, lr0[c][0]), t2s0[c][1]), lr_r);
+                }
+                ogp[c][0] = o0;
+                ogp[c][1] = o1;
             }
+
+            // ---- rotate --------------------------------------------------------------------------
+#pragma unroll
+            for (int c = 0; c < NC; c++)
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    sv_ud[c][k] = ud0[c][k];
+                    sv_dg[c][k] = dg0[c][k];
+                    gxP[c][k] = gx0[c][k];
+                    gyP[c][k] = gy0[c][k];
+                }
         }
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            yP[c][0] = yN[c][0];
+            yP[c][1] = yN[c][1];
+        }
+        okP2 = okP1;
+        okP1 = ok0;
     }
 
     // CTA reduction (fixed order => run-to-run deterministic), then the last-CTA fold
@@ -452,28 +511,31 @@ cudaError_t configure_kernels() {
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gradient<3, false>, GM_NT, 0);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gradient<3, false, true>, GM_NT, 0);
     if (e != cudaSuccess) return e;
     g_grad_slots = sms * (per_sm > 0 ? per_sm : 1);
     return cudaSuccess;
 }
 
+template <bool LOG, bool TGV>
+static void launch_gradient_nc(const FrameDev &F, float factor, dim3 grid, int rows, cudaStream_t s) {
+    switch (F.nc) {
+        case 1: k_gradient<1, LOG, TGV><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
+        case 2: k_gradient<2, LOG, TGV><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
+        default: k_gradient<3, LOG, TGV><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
+    }
+}
+
 cudaError_t launch_gradient(const FrameDev &F, float factor, cudaStream_t s) {
     int cx, bands, rows;
     grad_geometry(F.W, F.t1 - F.t0, &cx, &bands, &rows);
-    dim3 grid(cx, bands);
+    const dim3 grid(cx, bands);
     if (F.log_on) {
-        switch (F.nc) {
-            case 1: k_gradient<1, true><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
-            case 2: k_gradient<2, true><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
-            default: k_gradient<3, true><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
-        }
+        if (F.use_tgv) launch_gradient_nc<true, true>(F, factor, grid, rows, s);
+        else launch_gradient_nc<true, false>(F, factor, grid, rows, s);
     } else {
-        switch (F.nc) {
-            case 1: k_gradient<1, false><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
-            case 2: k_gradient<2, false><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
-            default: k_gradient<3, false><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
-        }
+        if (F.use_tgv) launch_gradient_nc<false, true>(F, factor, grid, rows, s);
+        else launch_gradient_nc<false, false>(F, factor, grid, rows, s);
     }
     return cudaGetLastError();
 }

@@ -107,7 +107,7 @@ static void par_memcpy(void *dst, const void *src, size_t bytes) {
     static const int nthreads = [] {
         const char *e = getenv("J2P_COPY_THREADS");
         const int v = e ? atoi(e) : 0;
-        return v > 0 && v <= 64 ? v : 4;
+        return v > 0 && v <= 64 ? v : 8;
     }();
 #pragma omp parallel for schedule(static) num_threads(nthreads) if (n > 2)
     for (long i = 0; i < n; i++) {

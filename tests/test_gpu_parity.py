@@ -60,6 +60,33 @@ def test_product_matches_oracle_random_planes(lib):
         H.assert_bit_identical(got, want, f'random seed {seed}')
 
 
+@pytest.mark.parametrize('case', ['tiny', 'patches', 'zero_coefs'])
+def test_guard_fallback_rows(lib, case):
+    """Values outside the proven range of the fast division / roots (numerics.cuh): the gradient
+    kernel must fall back to IEEE arithmetic for those rows and still match bit for bit.  compute()
+    takes the initial iterate from the caller, so the test plants the values there."""
+    img = synth.synth_coefs(200, 72, 40, '4:4:4', seed=4321)
+    f = H.decode_planes(img)
+    rng = np.random.default_rng(7)
+    if case == 'tiny':                       # every FISTA value far below 2^-35, some exactly 0
+        f = [(p * np.float32(2.0 ** -60) * (rng.random(p.shape) < 0.8)).astype(np.float32) for p in f]
+    elif case == 'patches':                  # a normal image with denormal, tiny and huge islands
+        for p, v in zip(f, (1e-42, 3e-13, 4e21)):
+            p[10:14, 30:90] = np.float32(v) * rng.standard_normal((4, 60)).astype(np.float32)
+            p[40:41, :] = np.float32(v)
+            p[50:60, 100:104] = 0.0
+    else:                                    # all-zero coefficients, unit tables: tiny values survive the projection
+        for pl in img.planes:
+            pl.data[:] = 0
+            pl.quant[:] = 1
+        f = [(rng.standard_normal(p.shape) * 1e-14).astype(np.float32) for p in f]
+    for iters in (1, 6):
+        fin = [p.copy() for p in f]
+        want = H.run_compute(_checker(), img, [0, 1, 2], 0.3, [0.001] * 3, iters, [p.copy() for p in fin])
+        got = H.run_compute('product', img, [0, 1, 2], 0.3, [0.001] * 3, iters, [p.copy() for p in fin])
+        H.assert_bit_identical(got, want, f'guard fallback {case} x{iters}')
+
+
 def test_config2_1080p_420_full_length(lib):
     """BASELINE config 2: 1920x1080 Q10 4:2:0, -i 100, all three planes.  Frame 1920x1088, luma
     grid 1080 rows (SURVEY headline 4).  Checked against the compiled reference when present

@@ -1,18 +1,7 @@
 #!/bin/bash
-# round-end evidence run on one GPU: staging-thread A/B, GPU tests, bench + ncu captures
+# A/B of k_gradient builds (per-kernel device time), then the GPU test suite on the default build
 mkdir -p gpurun_out
-for t in 4 8 16; do
-  echo "== J2P_COPY_THREADS=$t" >> gpurun_out/copy_ab.log
-  J2P_COPY_THREADS=$t timeout 200 python tools/e2e_trace.py 2>&1 | grep -v "^$" | tail -12 >> gpurun_out/copy_ab.log
-done
-tail -45 gpurun_out/copy_ab.log
+timeout 600 python tools/quick_time.py build_ab/lib_v6.so build_ab/lib_new_g3.so build_ab/lib_new_g4.so > gpurun_out/ab.log 2>&1
+cat gpurun_out/ab.log
 timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1
-tail -3 gpurun_out/pytest_gpu.log
-TAG=r01b
-export J2P_EXPECT_GPU=1
-python bench.py --steps 5 --warmup 3 > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err
-tail -c 2500 gpurun_out/bench_${TAG}.json
-tail -5 gpurun_out/bench_${TAG}.err
-ncu --metrics gpu__time_duration.sum --clock-control none -s 12 -c 32 --csv --log-file gpurun_out/launches_${TAG}.csv python tools/prof_driver.py > gpurun_out/ncu_list_${TAG}.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_gradient -s 4 -c 1 -o gpurun_out/prof_gradient_${TAG} -f python tools/prof_driver.py > gpurun_out/ncu_grad_${TAG}.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_project -s 12 -c 1 -o gpurun_out/prof_project_${TAG} -f python tools/prof_driver.py > gpurun_out/ncu_proj_${TAG}.log 2>&1
+tail -15 gpurun_out/pytest_gpu.log
