@@ -187,6 +187,11 @@ int j2p_session_objective(j2p_session *s, double out[4]);
 /* Block the host until everything queued on the session stream has finished. */
 int j2p_session_sync(j2p_session *s);
 
+/* Make a freshly allocated host buffer resident (huge-page hint + parallel first touch).  The
+ * drop-in compute() calls it for the result buffers it hands back (compute.c:458) while the device
+ * is still iterating, so the page faults of 100 MB of new memory are off the download path. */
+void j2p_host_prefault(void *p, size_t bytes);
+
 /* Raw handles for callers that schedule their own work around the session (bench timing with
  * CUDA events on the launching stream; torch interop).  The stream is a cudaStream_t. */
 void *j2p_session_stream(j2p_session *s);

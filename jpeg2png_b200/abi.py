@@ -191,7 +191,7 @@ HEADER_SYMBOLS = [
     'j2p_session_width', 'j2p_session_height', 'j2p_session_upload', 'j2p_session_reset',
     'j2p_session_iterate', 'j2p_session_profile', 'j2p_session_wait_iteration', 'j2p_session_download', 'j2p_session_set_logging',
     'j2p_session_objective', 'j2p_session_sync', 'j2p_session_stream', 'j2p_session_plane_ptr',
-    'j2p_session_launches', 'j2p_version',
+    'j2p_session_launches', 'j2p_version', 'j2p_host_prefault',
 ]
 
 _product = None

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient(const __g
     const int X0 = (blockIdx.x * GM_WARPS + wid) * GM_USE;   // first target column of this warp
     const int yb = F.t0 + blockIdx.y * band_rows;            // first target row of this CTA (local row index)
     const int ye = min(yb + band_rows, F.t1);
-    const int s_last = F.Hg - 1 - F.y0g, s_first = -F.y0g;   // local indices of the frame's last / first row
+    const int s_first = -F.y0g;                              // local index of the frame's first row
     const int px0 = X0 - 2 + 2 * lane;                       // even; W is even => the pair is in or out together
     const bool pair_in = px0 >= 0 && px0 < W;
     const bool is_target = pair_in && lane >= 1 && lane <= 30;
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient(const __g
     const int pxc = pair_in ? px0 : 0;
     auto issue_row_loads = [&](int row) {
         const int rc = min(max(row, 0), H - 1);
-        const size_t gi = (size_t)rc * W + pxc;
+        const unsigned gi = (unsigned)rc * (unsigned)W + (unsigned)pxc;   // frames are far below 2^32 pixels (checked at session creation)
 #pragma unroll
         for (int c = 0; c < NC; c++) {
             ldx[c] = *reinterpret_cast<const float2 *>(F.pl[c].x + gi);
@@ -205,10 +205,10 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient(const __g
         {
             const int s = i - 1;
             const bool src_in = pair_in && s >= 0 && s < H;
-            if (s >= s_last) {                                  // no row below in the frame: gy := 0 (compute.c:81)
-#pragma unroll
-                for (int c = 0; c < NC; c++) { yN[c][0] = yP[c][0]; yN[c][1] = yP[c][1]; }
-            }
+            // No row below the frame's last row: gy := 0 (compute.c:81).  Nothing to do for it: the
+            // row loads are clamped into the buffer, whose last row IS the frame's last row whenever
+            // that row is reachable (a strip that does not end the frame carries halo rows below),
+            // so row s+1 re-reads row s, the FISTA point comes out bit-identical and gy0 = +0.
 
             // ---- source row s: TV (compute.c:79-105) -------------------------------------------
             float gx0[NC][2], gy0[NC][2], tvs0[NC][2], tvr0[NC][2], tvb0[NC][2];
@@ -286,10 +286,12 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient(const __g
             float t2s0[NC][2], lr0[NC][2], ud0[NC][2], dg0[NC][2];
             if (TGV) {
                 if (s <= s_first) {                             // no row above in the frame: gxy, gyy := 0 (compute.c:141-143)
+                    // gxy needs no help: the clamped loads made "row -1" a copy of row 0, so the gx
+                    // saved from the previous step already equals gx0.  gy of that copy is 0, not gy0.
 #pragma unroll
                     for (int c = 0; c < NC; c++)
 #pragma unroll
-                        for (int k = 0; k < 2; k++) { gxP[c][k] = gx0[c][k]; gyP[c][k] = gy0[c][k]; }
+                        for (int k = 0; k < 2; k++) gyP[c][k] = gy0[c][k];
                 }
                 float gxx[NC][2], gyy[NC][2], sym[NC][2];
                 float n2[2] = {0.f, 0.f};
@@ -371,7 +373,7 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient(const __g
                     }
                 }
                 if (is_target) {
-                    const size_t gi = (size_t)(s - 1) * W + px0;
+                    const unsigned gi = (unsigned)(s - 1) * (unsigned)W + (unsigned)px0;
 #pragma unroll
                     for (int c = 0; c < NC; c++) {
                         *reinterpret_cast<float2 *>(F.pl[c].g + gi) = make_float2(o[c][0], o[c][1]);

@@ -19,11 +19,13 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
 
 #include <mutex>
 #include <vector>
 
 #include "../../include/jpeg2png_b200.h"
+#include "copy_pool.h"
 #include "kernels.cuh"
 
 namespace j2p {
@@ -69,8 +71,8 @@ static void dev_free(void *p, cudaStream_t st) {
 }
 
 // ---- host <-> device staging for pageable caller memory (the reference's struct coef buffers are
-// malloc-family memory): 8 MB pinned chunks, double buffered, the pageable side copied with all
-// host threads (this also parallelises the first-touch page faults of a fresh result buffer).
+// malloc-family memory): 8 MB pinned chunks, double buffered, the pageable side copied by the
+// threads of copy_pool.h.
 constexpr size_t kStageChunk = 8u << 20;
 struct PinnedPool {
     std::mutex mu;
@@ -98,22 +100,19 @@ struct PinnedPool {
 };
 static PinnedPool g_pinned;
 
-static void par_memcpy(void *dst, const void *src, size_t bytes) {
-    const size_t piece = 1u << 20;
-    const long n = (long)((bytes + piece - 1) / piece);
-    // a small team: one as wide as the machine (128 hardware threads on the GPU boxes) spends two
-    // orders of magnitude longer waking up than copying (profiles/r01_notes.md).  J2P_COPY_THREADS
-    // overrides the default for tuning.
-    static const int nthreads = [] {
-        const char *e = getenv("J2P_COPY_THREADS");
-        const int v = e ? atoi(e) : 0;
-        return v > 0 && v <= 64 ? v : 8;
-    }();
-#pragma omp parallel for schedule(static) num_threads(nthreads) if (n > 2)
-    for (long i = 0; i < n; i++) {
-        const size_t off = (size_t)i * piece;
-        memcpy((char *)dst + off, (const char *)src + off, bytes - off < piece ? bytes - off : piece);
-    }
+static void par_memcpy(void *dst, const void *src, size_t bytes) { CopyPool::instance().copy(dst, src, bytes); }
+
+// Make a freshly allocated host buffer resident before it is needed: ask for huge pages where the
+// kernel offers them on request, then first-touch every page with the copy threads.  compute()
+// calls this for its result buffers while the device is still iterating.
+extern "C" void j2p_host_prefault(void *p, size_t bytes) {
+    if (!p || bytes == 0) return;
+#ifdef MADV_HUGEPAGE
+    const uintptr_t huge = (uintptr_t)2u << 20;
+    const uintptr_t a = ((uintptr_t)p + huge - 1) & ~(huge - 1), e = ((uintptr_t)p + bytes) & ~(huge - 1);
+    if (e > a) madvise((void *)a, (size_t)(e - a), MADV_HUGEPAGE);      // a hint; failure is harmless
+#endif
+    CopyPool::instance().touch(p, bytes);
 }
 
 struct j2p_session {

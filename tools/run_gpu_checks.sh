@@ -1,7 +1,11 @@
 #!/bin/bash
-# A/B of k_gradient builds (per-kernel device time), then the GPU test suite on the default build
+# host bandwidth diagnosis + e2e phases at several staging thread counts
 mkdir -p gpurun_out
-timeout 600 python tools/quick_time.py build_ab/lib_v6.so build_ab/lib_new_g3.so build_ab/lib_new_g4.so > gpurun_out/ab.log 2>&1
-cat gpurun_out/ab.log
-timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1
-tail -15 gpurun_out/pytest_gpu.log
+timeout 300 python tools/host_bw.py > gpurun_out/host_bw.log 2>&1
+cat gpurun_out/host_bw.log
+rm -f gpurun_out/copy_ab.log
+for t in 1 2 4 8; do
+  echo "== J2P_COPY_THREADS=$t" >> gpurun_out/copy_ab.log
+  J2P_COPY_THREADS=$t timeout 200 python tools/e2e_trace.py 2>&1 | grep -v "^$" | tail -7 >> gpurun_out/copy_ab.log
+done
+cat gpurun_out/copy_ab.log
