@@ -152,8 +152,9 @@ unsigned j2p_session_height(const j2p_session *s);
 
 /* Host -> HBM.  `data`: int16 [blocks][64]; `quant`: uint16[64]; `fdata`: raster plane_h x plane_w
  * conventional decode.  Performs the reference aux_init (compute.c:278-310) on the device:
- * cos = data*quant, nearest-neighbour upsample with edge clamp, fista = fdata.  Asynchronous on
- * the session stream when the host buffers are pinned. */
+ * cos = data*quant, nearest-neighbour upsample with edge clamp, fista = fdata.  Returns as soon
+ * as the host arrays have been read (into the session's pinned staging ring): the caller may free
+ * them; the DMA of the last chunks and the set-up kernels are still queued on the session stream. */
 int j2p_session_upload(j2p_session *s, unsigned channel, const int16_t *data,
                        const uint16_t *quant, const float *fdata);
 

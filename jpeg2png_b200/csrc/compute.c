@@ -58,6 +58,20 @@ static double now_ms(void) {
         return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
+/* free the consumed input buffers that could not be recycled and make the result buffers that are
+ * still missing (alloc_simd contract, utils.h:89-98), pages already touched */
+static void host_buffers(unsigned nchannel, float **consumed, float **outs, size_t out_bytes) {
+        for (unsigned c = 0; c < nchannel; c++) {
+                free(consumed[c]);
+                consumed[c] = NULL;
+                if (!outs[c]) {
+                        outs[c] = aligned_alloc(16, out_bytes);
+                        if (!outs[c]) die("allocation error");
+                        j2p_host_prefault(outs[c], out_bytes);
+                }
+        }
+}
+
 /* how many iterations may be queued on the device ahead of the progress bar */
 #define J2P_PROGRESS_LAG 8u
 
@@ -93,33 +107,35 @@ void compute(unsigned nchannel, struct coef *coefs, struct logger *log, struct p
         const int want_log = log && log->f != NULL;
         if (want_log && j2p_session_set_logging(s, 1) != J2P_OK) die("%s", j2p_last_error());
 
+        /* Buffer ownership as in the reference: the caller's fdata is consumed (compute.c:304-305)
+         * and a malloc-family buffer of frame size comes back (compute.c:458).  Where a plane
+         * already has frame size (4:4:4 planes, luma) the consumed buffer IS the one handed back —
+         * no free, no allocation, no page faults.  Otherwise the free (an munmap: ~5 ms for a 4K
+         * plane on the 128-thread hosts) and the allocation + first touch of the new buffer are
+         * done while the device iterates, not on the transfer path. */
+        const unsigned w = j2p_session_width(s), h = j2p_session_height(s);
+        size_t out_bytes = (size_t)w * h * sizeof(float);
+        out_bytes = (out_bytes + 15) & ~(size_t)15;
+        float *outs[3] = {NULL, NULL, NULL}, *consumed[3] = {NULL, NULL, NULL};
         for (unsigned c = 0; c < nchannel; c++) {
                 if (j2p_session_upload(s, c, coefs[c].data, coefs[c].quant_table, coefs[c].fdata) != J2P_OK)
                         die("%s", j2p_last_error());
-                free(coefs[c].fdata);                                   /* compute.c:304-305 */
+                if (coefs[c].fdata && (size_t)coefs[c].w * coefs[c].h == (size_t)w * h) outs[c] = coefs[c].fdata;
+                else consumed[c] = coefs[c].fdata;
                 coefs[c].fdata = NULL;
         }
 
         if (trace) { t1 = now_ms(); fprintf(stderr, "j2p trace: upload %.2f ms\n", t1 - t0); t0 = t1; }
-        /* Result buffers (compute.c:458: new alloc_simd memory owned by the caller).  They are
-         * allocated and first-touched once a few iterations are queued, so that the kernel's
-         * page zeroing overlaps the device's work instead of the download. */
-        const unsigned w = j2p_session_width(s), h = j2p_session_height(s);
-        size_t out_bytes = (size_t)w * h * sizeof(float);
-        out_bytes = (out_bytes + 15) & ~(size_t)15;
-        float *outs[3] = {NULL, NULL, NULL};
-        const unsigned prefault_at = iterations > 16 ? 15 : (iterations ? iterations - 1 : 0);
+        const unsigned housekeeping_at = iterations > 16 ? 15 : (iterations ? iterations - 1 : 0);
+        int housekeeping_done = 0;
 
         unsigned reported = 0;
         for (unsigned i = 0; i < iterations; i++) {
                 if (log) log->iteration = i;                            /* compute.c:428 */
                 if (j2p_session_iterate(s, i, 1) != J2P_OK) die("%s", j2p_last_error());
-                if (i == prefault_at) {
-                        for (unsigned c = 0; c < nchannel; c++) {
-                                outs[c] = aligned_alloc(16, out_bytes);  /* utils.h:89-98 */
-                                if (!outs[c]) die("allocation error");
-                                j2p_host_prefault(outs[c], out_bytes);
-                        }
+                if (i == housekeeping_at) {
+                        host_buffers(nchannel, consumed, outs, out_bytes);
+                        housekeeping_done = 1;
                 }
                 if (want_log) {
                         double o[4];
@@ -148,14 +164,10 @@ void compute(unsigned nchannel, struct coef *coefs, struct logger *log, struct p
                 j2p_session_sync(s);
                 t1 = now_ms(); fprintf(stderr, "j2p trace: device drain %.2f ms\n", t1 - t0); t0 = t1;
         }
+        if (!housekeeping_done) host_buffers(nchannel, consumed, outs, out_bytes);   /* iterations == 0 */
         for (unsigned c = 0; c < nchannel; c++) {                       /* compute.c:455-463 */
-                float *out = outs[c];
-                if (!out) {                                             /* iterations == 0 */
-                        out = aligned_alloc(16, out_bytes);             /* utils.h:89-98 */
-                        if (!out) die("allocation error");
-                }
-                if (j2p_session_download(s, c, out) != J2P_OK) die("%s", j2p_last_error());
-                coefs[c].fdata = out;
+                if (j2p_session_download(s, c, outs[c]) != J2P_OK) die("%s", j2p_last_error());
+                coefs[c].fdata = outs[c];
                 coefs[c].w = w;
                 coefs[c].h = h;
         }

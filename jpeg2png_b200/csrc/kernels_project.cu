@@ -292,7 +292,9 @@ __global__ void __launch_bounds__(P_NT, (SW * SH <= 1) ? J2P_PROJ_MIN_CTAS : 2) 
 // set-up kernels
 // ------------------------------------------------------------------------------------------
 // conventional decode of one plane: dequantise + IDCT + raster (jpeg.c:83-92, jpeg2png.c:131-139)
-__global__ void __launch_bounds__(P_NT) k_decode(const int16_t *data, const float *q /*[64] device*/, float *out, int cw, int ch) {
+struct QTable { float q[64]; };                                             // by value: 256 B of kernel parameters, no device copy to manage
+__global__ void __launch_bounds__(P_NT) k_decode(const int16_t *data, const __grid_constant__ QTable qt, float *out, int cw, int ch) {
+    const float *q = qt.q;
     __shared__ __align__(16) float tiles[P_NT / 8][TILE_STRIDE];
     const int tid = threadIdx.x, b = tid >> 3, j = tid & 7;
     const int nb = (cw >> 3) * (ch >> 3);
@@ -607,9 +609,11 @@ cudaError_t launch_project(const FrameDev &Fin, float factor, cudaStream_t s) {
     return cudaSuccess;
 }
 
-cudaError_t launch_decode(const int16_t *data, const float *q_dev, float *out, int cw, int ch, cudaStream_t s) {
+cudaError_t launch_decode(const int16_t *data, const float *q_host, float *out, int cw, int ch, cudaStream_t s) {
     const int nb = (cw / 8) * (ch / 8);
-    k_decode<<<(nb + P_NT / 8 - 1) / (P_NT / 8), P_NT, 0, s>>>(data, q_dev, out, cw, ch);
+    QTable qt;
+    for (int i = 0; i < 64; i++) qt.q[i] = q_host[i];
+    k_decode<<<(nb + P_NT / 8 - 1) / (P_NT / 8), P_NT, 0, s>>>(data, qt, out, cw, ch);
     return cudaGetLastError();
 }
 

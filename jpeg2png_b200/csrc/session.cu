@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/mman.h>
+#include <time.h>
 
 #include <mutex>
 #include <vector>
@@ -34,7 +35,7 @@ cudaError_t configure_kernels();
 cudaError_t launch_gradient(const FrameDev &F, float factor, cudaStream_t s);
 cudaError_t launch_project(const FrameDev &F, float factor, cudaStream_t s);
 cudaError_t launch_fold_sums(const double *sums_by_rank, int nranks, int nc, float *norms, cudaStream_t s);
-cudaError_t launch_decode(const int16_t *data, const float *q_dev, float *out, int cw, int ch, cudaStream_t s);
+cudaError_t launch_decode(const int16_t *data, const float *q_host, float *out, int cw, int ch, cudaStream_t s);
 cudaError_t launch_init_plane(const float *fdata, float *x, float *xp, int W, int H, int cw, int ch, int sw, int sh,
                               cudaStream_t s);
 }  // namespace j2p
@@ -74,6 +75,7 @@ static void dev_free(void *p, cudaStream_t st) {
 // malloc-family memory): 8 MB pinned chunks, double buffered, the pageable side copied by the
 // threads of copy_pool.h.
 constexpr size_t kStageChunk = 8u << 20;
+constexpr int kStageSlots = 4;
 struct PinnedPool {
     std::mutex mu;
     std::vector<void *> free_list;
@@ -120,7 +122,7 @@ struct j2p_session {
     cudaStream_t stream = nullptr;
     FrameDev F{};
     j2p_frame_desc desc{};
-    float *x[3] = {}, *xp[3] = {}, *g[3] = {}, *gp[3] = {}, *fdata0[3] = {}, *qdev[3] = {};
+    float *x[3] = {}, *xp[3] = {}, *g[3] = {}, *gp[3] = {}, *fdata0[3] = {};
     int16_t *data[3] = {};
     bool uploaded[3] = {};
     bool strip = false;       // row strip of a larger frame (multi-GPU tiling)
@@ -134,6 +136,9 @@ struct j2p_session {
     unsigned long long next_log_iter = 0;
     cudaEvent_t ev[kEventRing] = {};
     long long ev_iter[kEventRing];
+    void *stage[kStageSlots] = {};            // pinned staging ring (lazily taken from the process-wide pool)
+    cudaEvent_t stage_ev[kStageSlots] = {};
+    unsigned stage_next = 0;
 };
 
 static std::once_flag g_cfg_once[64];
@@ -164,13 +169,17 @@ extern "C" void j2p_session_destroy(j2p_session *s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (int c = 0; c < 3; c++) {
         dev_free(s->x[c], s->stream); dev_free(s->xp[c], s->stream); dev_free(s->g[c], s->stream); dev_free(s->gp[c], s->stream);
-        dev_free(s->fdata0[c], s->stream); dev_free(s->qdev[c], s->stream); dev_free(s->data[c], s->stream);
+        dev_free(s->fdata0[c], s->stream); dev_free(s->data[c], s->stream);
     }
     dev_free(s->F.partials, s->stream); dev_free(s->F.norms, s->stream); dev_free(s->F.counter, s->stream);
     dev_free(s->F.sums, s->stream); dev_free(s->F.logsums, s->stream);
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (int i = 0; i < kEventRing; i++)
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    for (int k = 0; k < kStageSlots; k++) {          // the stream is idle: no DMA touches the ring any more
+        if (s->stage_ev[k]) cudaEventDestroy(s->stage_ev[k]);
+        if (s->stage[k]) g_pinned.put(s->stage[k]);
+    }
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -266,7 +275,6 @@ static int create_impl(j2p_session *s, int device, const j2p_frame_desc *d, unsi
         CK(dev_alloc(&s->gp[c], nc * sizeof(float), s->stream));
         CK(dev_alloc(&s->fdata0[c], nc * sizeof(float), s->stream));
         CK(dev_alloc(&s->data[c], nc * sizeof(int16_t), s->stream));
-        CK(dev_alloc(&s->qdev[c], 64 * sizeof(float), s->stream));
         P.x = s->x[c]; P.xp = s->xp[c]; P.g = s->g[c]; P.gp = s->gp[c]; P.data = s->data[c];
     }
     F.grad_ctas = grad_cta_count(F.W, F.t1 - F.t0);
@@ -333,57 +341,83 @@ extern "C" int j2p_session_reset(j2p_session *s) {
     return reset_impl(s);
 }
 
-// pageable host -> device through the pinned double buffer, on the session stream
-static int staged_h2d(j2p_session *s, void *dst, const void *src, size_t bytes) {
-    void *buf[2] = {g_pinned.get(), g_pinned.get()};
-    cudaEvent_t ev[2] = {nullptr, nullptr};
-    int rc = J2P_OK;
-    if (!buf[0] || !buf[1]) rc = fail(J2P_ERR_CUDA, "pinned staging allocation failed");
-    for (int k = 0; k < 2 && rc == J2P_OK; k++)
-        if (cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) != cudaSuccess) rc = fail(J2P_ERR_CUDA, "cudaEventCreate failed");
-    size_t off = 0;
-    for (int k = 0; off < bytes && rc == J2P_OK; k ^= 1) {
-        const size_t n = bytes - off < kStageChunk ? bytes - off : kStageChunk;
-        if (cudaEventSynchronize(ev[k]) != cudaSuccess) { rc = fail(J2P_ERR_CUDA, "cudaEventSynchronize failed"); break; }
-        par_memcpy(buf[k], (const char *)src + off, n);
-        if (cudaMemcpyAsync((char *)dst + off, buf[k], n, cudaMemcpyHostToDevice, s->stream) != cudaSuccess ||
-            cudaEventRecord(ev[k], s->stream) != cudaSuccess) { rc = fail(J2P_ERR_CUDA, "staged H2D copy failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
-        off += n;
+// J2P_TRACE=1: where the host time of the transfers goes (stderr; measurement aid)
+static bool trace_on() {
+    static const bool on = [] { const char *e = getenv("J2P_TRACE"); return e && *e == '1'; }();
+    return on;
+}
+static double now_ms() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+// ---- staging ring: four pinned 8 MB buffers per session, each with the event of the last DMA that
+// used it.  A transfer of any size walks the ring; nothing drains between the arrays of an upload,
+// so the host copy of one array overlaps the DMA of the previous one.
+static int stage_slot(j2p_session *s, int *slot_out) {
+    const int k = (int)(s->stage_next++ % kStageSlots);
+    if (!s->stage[k]) {
+        s->stage[k] = g_pinned.get();
+        if (!s->stage[k]) return fail(J2P_ERR_CUDA, "pinned staging allocation failed");
+        CK(cudaEventCreateWithFlags(&s->stage_ev[k], cudaEventDisableTiming));
     }
-    for (int k = 0; k < 2; k++) {
-        if (ev[k]) { cudaEventSynchronize(ev[k]); cudaEventDestroy(ev[k]); }
-        if (buf[k]) g_pinned.put(buf[k]);
-    }
-    return rc;
+    CK(cudaEventSynchronize(s->stage_ev[k]));         // the buffer's previous DMA is done (no-op if never recorded)
+    *slot_out = k;
+    return J2P_OK;
 }
 
-// device -> pageable host, same scheme; returns when `dst` is complete
+// pageable host -> device on the session stream.  Returns when `src` has been read completely
+// (the caller may free it); the DMA of the last chunks may still be in flight.
+static int staged_h2d(j2p_session *s, void *dst, const void *src, size_t bytes) {
+    const double t_begin = now_ms();
+    double t_wait = 0., t_copy = 0.;
+    for (size_t off = 0; off < bytes;) {
+        const size_t n = bytes - off < kStageChunk ? bytes - off : kStageChunk;
+        int k;
+        const double t0 = now_ms();
+        const int rc = stage_slot(s, &k);
+        if (rc != J2P_OK) return rc;
+        const double t1 = now_ms();
+        par_memcpy(s->stage[k], (const char *)src + off, n);
+        t_wait += t1 - t0;
+        t_copy += now_ms() - t1;
+        CK(cudaMemcpyAsync((char *)dst + off, s->stage[k], n, cudaMemcpyHostToDevice, s->stream));
+        CK(cudaEventRecord(s->stage_ev[k], s->stream));
+        off += n;
+    }
+    if (trace_on())
+        fprintf(stderr, "j2p trace:   h2d %zu B: %.2f ms (waiting for a buffer %.2f, host copy %.2f)\n", bytes, now_ms() - t_begin, t_wait, t_copy);
+    return J2P_OK;
+}
+
+// device -> pageable host; returns when `dst` is complete
 static int staged_d2h(j2p_session *s, void *dst, const void *src, size_t bytes) {
-    void *buf[2] = {g_pinned.get(), g_pinned.get()};
-    cudaEvent_t ev[2] = {nullptr, nullptr};
-    int rc = J2P_OK;
-    if (!buf[0] || !buf[1]) rc = fail(J2P_ERR_CUDA, "pinned staging allocation failed");
-    for (int k = 0; k < 2 && rc == J2P_OK; k++)
-        if (cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) != cudaSuccess) rc = fail(J2P_ERR_CUDA, "cudaEventCreate failed");
     const size_t nchunks = (bytes + kStageChunk - 1) / kStageChunk;
-    auto issue = [&](size_t i) -> bool {
-        const size_t off = i * kStageChunk, n = bytes - off < kStageChunk ? bytes - off : kStageChunk;
-        return cudaMemcpyAsync(buf[i & 1], (const char *)src + off, n, cudaMemcpyDeviceToHost, s->stream) == cudaSuccess &&
-               cudaEventRecord(ev[i & 1], s->stream) == cudaSuccess;
+    int slot[kStageSlots];
+    // keep up to kStageSlots - 1 DMAs in flight ahead of the host copy
+    size_t issued = 0;
+    auto issue = [&]() -> int {
+        const size_t off = issued * kStageChunk, n = bytes - off < kStageChunk ? bytes - off : kStageChunk;
+        int k;
+        const int rc = stage_slot(s, &k);
+        if (rc != J2P_OK) return rc;
+        CK(cudaMemcpyAsync(s->stage[k], (const char *)src + off, n, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaEventRecord(s->stage_ev[k], s->stream));
+        slot[issued % kStageSlots] = k;
+        issued++;
+        return J2P_OK;
     };
-    if (rc == J2P_OK && nchunks > 0 && !issue(0)) rc = fail(J2P_ERR_CUDA, "staged D2H copy failed");
-    for (size_t i = 0; i < nchunks && rc == J2P_OK; i++) {
-        if (i + 1 < nchunks && !issue(i + 1)) { rc = fail(J2P_ERR_CUDA, "staged D2H copy failed"); break; }
-        if (cudaEventSynchronize(ev[i & 1]) != cudaSuccess) { rc = fail(J2P_ERR_CUDA, "cudaEventSynchronize failed"); break; }
+    for (size_t i = 0; i < nchunks; i++) {
+        while (issued < nchunks && issued < i + (size_t)(kStageSlots - 1)) {
+            const int rc = issue();
+            if (rc != J2P_OK) return rc;
+        }
+        const int k = slot[i % kStageSlots];
+        CK(cudaEventSynchronize(s->stage_ev[k]));
         const size_t off = i * kStageChunk, n = bytes - off < kStageChunk ? bytes - off : kStageChunk;
-        par_memcpy((char *)dst + off, buf[i & 1], n);
+        par_memcpy((char *)dst + off, s->stage[k], n);
     }
-    cudaStreamSynchronize(s->stream);
-    for (int k = 0; k < 2; k++) {
-        if (ev[k]) cudaEventDestroy(ev[k]);
-        if (buf[k]) g_pinned.put(buf[k]);
-    }
-    return rc;
+    return J2P_OK;
 }
 
 extern "C" int j2p_session_upload(j2p_session *s, unsigned c, const int16_t *data, const uint16_t *quant,
@@ -394,26 +428,23 @@ extern "C" int j2p_session_upload(j2p_session *s, unsigned c, const int16_t *dat
     FrameDev &F = s->F;
     PlaneDev &P = F.pl[c];
     const size_t nc = (size_t)P.cw * P.ch;
-    float qf[64];
     for (int j = 0; j < 64; j++) {
         if (quant[j] == 0) return fail(J2P_ERR_ARG, "invalid quantization table (zero entry, jpeg.c:41-45)");
-        qf[j] = (float)quant[j];
-        F.q[c][j] = qf[j];
-        F.qq[c][j] = qf[j] * qf[j];                                     // fp32 product (compute.c:49)
+        F.q[c][j] = (float)quant[j];
+        F.qq[c][j] = F.q[c][j] * F.q[c][j];                             // fp32 product (compute.c:49)
         F.rqq[c][j] = (float)(1.0 / (double)F.qq[c][j]);                // RN(1/qq): fp64 quotient narrowed once is correctly rounded
     }
-    CK(cudaMemcpyAsync(s->qdev[c], qf, sizeof qf, cudaMemcpyHostToDevice, s->stream));
     int rcs = staged_h2d(s, s->data[c], data, nc * sizeof(int16_t));
     if (rcs != J2P_OK) return rcs;
     if (fdata) {
         rcs = staged_h2d(s, s->fdata0[c], fdata, nc * sizeof(float));
         if (rcs != J2P_OK) return rcs;
     } else {
-        CK(launch_decode(s->data[c], s->qdev[c], s->fdata0[c], P.cw, P.ch, s->stream));
+        CK(launch_decode(s->data[c], F.q[c], s->fdata0[c], P.cw, P.ch, s->stream));
         s->launches++;
     }
-    // qf lives on this stack frame: make sure the (pageable, hence already staged) copy is done
-    CK(cudaStreamSynchronize(s->stream));
+    // The host arrays have been read completely (they sit in the pinned ring or on the device);
+    // the stream is NOT drained here, so the next plane's host copy overlaps this plane's DMA.
     s->uploaded[c] = true;
     bool all = true;
     for (int k = 0; k < F.nc; k++) all = all && s->uploaded[k];
