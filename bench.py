@@ -298,6 +298,15 @@ def run_product_arm(args, rank, local_rank, world):
     checksum = float(np.float64(out).sum())
     lib.j2p_session_destroy(s)
 
+    # The clock sampler covers the device-timed region above.  It is stopped before the end-to-end
+    # leg: a polling nvidia-smi takes driver locks that stall the CUDA API calls of this process,
+    # and the e2e leg is exactly the host-API path (measured: 65 ms per 4K solve with the poller
+    # running, 36 ms without; profiles/r01_notes.md).  J2P_BENCH_SAMPLE_E2E=1 keeps it running.
+    keep_sampling = os.environ.get('J2P_BENCH_SAMPLE_E2E') == '1'
+    if sampler is not None and not keep_sampling:
+        stop.set()
+        sampler.join(timeout=3)
+
     # ---- end to end through compute() with host buffers --------------------------------------
     # the conventional decode the caller of compute() owns (jpeg2png.c:127-139): produced once,
     # outside the timed region, by the product's own device decode
@@ -320,8 +329,7 @@ def run_product_arm(args, rank, local_rank, world):
     e2e_checksum = float(np.float64(arrays[1].result(0)).sum())
     for a in arrays:
         a.release()
-
-    if sampler is not None:
+    if sampler is not None and keep_sampling:
         stop.set()
         sampler.join(timeout=3)
 
@@ -363,7 +371,7 @@ def run_product_arm(args, rank, local_rank, world):
             'config': {'workload': WORKLOAD, 'frames_per_step': world, 'sharding': 'one frame per GPU, no data-path collective',
                        'l2': 'working set ~0.75 GB per frame >> 126 MB L2 (no flush needed)',
                        'frame': [W, H], 'iterations': ITERATIONS},
-            'clocks': summarise_clocks(clock_lines),
+            'clocks': dict(summarise_clocks(clock_lines), region='device-timed region' + (' and e2e leg' if keep_sampling else ' (poller stopped before the e2e leg)')),
             'e2e': {'value': e2e_value, 'unit': 'Mpix-it/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                     'ms_per_step': e2e_s / n_e2e * 1e3, 'host_memory': 'pageable malloc-family buffers (reference struct coef contract)',
                     'api': 'compute(3, coefs, log, NULL, 0.3, pweights, 100) via libjpeg2png_b200.so'},

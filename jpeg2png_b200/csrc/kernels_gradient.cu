@@ -58,6 +58,12 @@ struct TvSlow {
     float q[3][NC][2];              // out: self / right / below quotients (compute.c:98-103)
     float n[2];                     // out: the norms (for the objective log)
 };
+// A value read back from local memory after the fallback call is passed through one ALU
+// instruction inside the cold branch.  Without it the first instruction after the join waits on
+// the scoreboard the compiler gave those local loads — the same one the row prefetch uses — and
+// every row stalls there until its prefetch has landed (15 % of all stall samples, 5 us per 4K
+// iteration; profiles/r01_notes.md).  `zero` is 0, but not to the compiler.
+__device__ __forceinline__ float settle(float v, unsigned zero) { return __uint_as_float(__float_as_uint(v) ^ zero); }
 template <int NC>
 __device__ __noinline__ void tv_slow(TvSlow<NC> *io, float a1, bool src_in) {
     for (int k = 0; k < 2; k++) {
@@ -115,6 +121,7 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient(const __g
     const bool is_target = pair_in && lane >= 1 && lane <= 30;
     const bool has_l0 = px0 > 0, has_r1 = px0 + 1 < W - 1;   // k=1 always has a left neighbour, k=0 a right one
     const float a1 = F.a1, a2 = F.a2, a2m2 = fmul(-2.f, F.a2);
+    const unsigned zero = (unsigned)band_rows >> 31;         // see settle()
 
     double acc[NC];
     double tv_acc = 0., tv2_acc = 0.;
@@ -256,7 +263,7 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient(const __g
 #pragma unroll
                     for (int c = 0; c < NC; c++)
 #pragma unroll
-                        for (int k = 0; k < 2; k++) { tvs0[c][k] = io.q[0][c][k]; tvr0[c][k] = io.q[1][c][k]; tvb0[c][k] = io.q[2][c][k]; }
+                        for (int k = 0; k < 2; k++) { tvs0[c][k] = settle(io.q[0][c][k], zero); tvr0[c][k] = settle(io.q[1][c][k], zero); tvb0[c][k] = settle(io.q[2][c][k], zero); }
                     if (LOG && is_target && s >= yb && s < ye) tv_acc = __dadd_rn(__dadd_rn(tv_acc, (double)fmul(a1, io.n[0])), (double)fmul(a1, io.n[1]));
                 }
             }
@@ -349,7 +356,7 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient(const __g
 #pragma unroll
                     for (int c = 0; c < NC; c++)
 #pragma unroll
-                        for (int k = 0; k < 2; k++) { t2s0[c][k] = io.q[0][c][k]; lr0[c][k] = io.q[1][c][k]; ud0[c][k] = io.q[2][c][k]; dg0[c][k] = io.q[3][c][k]; }
+                        for (int k = 0; k < 2; k++) { t2s0[c][k] = settle(io.q[0][c][k], zero); lr0[c][k] = settle(io.q[1][c][k], zero); ud0[c][k] = settle(io.q[2][c][k], zero); dg0[c][k] = settle(io.q[3][c][k], zero); }
                     if (LOG && is_target && s >= yb && s < ye) tv2_acc = __dadd_rn(__dadd_rn(tv2_acc, (double)fmul(a2, io.n[0])), (double)fmul(a2, io.n[1]));
                 }
             } else {

@@ -22,7 +22,9 @@
 #include <sys/mman.h>
 #include <time.h>
 
+#include <map>
 #include <mutex>
+#include <utility>
 #include <vector>
 
 #include "../../include/jpeg2png_b200.h"
@@ -61,15 +63,35 @@ static int fail(int code, const char *fmt, ...) {
 
 constexpr int kEventRing = 32;
 
-// ---- device memory: stream-ordered allocation from the device's default pool, which is told to
-// keep what it is given back (release threshold = max).  A compute() call therefore pays for
-// cudaMalloc only the first time a frame size is seen, and never for a device-wide cudaFree sync.
-static cudaError_t dev_alloc(void **p, size_t bytes, cudaStream_t st) { return cudaMallocAsync(p, bytes ? bytes : 16, st); }
-template <typename T>
-static cudaError_t dev_alloc(T **p, size_t bytes, cudaStream_t st) { return dev_alloc(reinterpret_cast<void **>(p), bytes, st); }
-static void dev_free(void *p, cudaStream_t st) {
-    if (p) cudaFreeAsync(p, st);
-}
+// ---- device memory: a process-wide cache of device blocks keyed by (device, exact size).  A
+// session takes its ~25 blocks from it and gives them back when it is destroyed (its stream is
+// idle by then), so a compute() call pays for cudaMalloc only the first time a frame size is seen
+// and never for cudaFree's device-wide synchronisation.  (cudaMallocAsync with an unbounded
+// release threshold did the same on paper; inside a process that also runs PyTorch its calls
+// took 10-50 ms per session, profiles/r01_notes.md.)
+struct DevCache {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void *> blocks;
+    size_t held = 0;
+    static constexpr size_t kCap = (size_t)24 << 30;                   // bytes kept at most; beyond that blocks are freed
+    void *get(int dev, size_t bytes) {
+        std::lock_guard<std::mutex> l(mu);
+        auto it = blocks.find({dev, bytes});
+        if (it == blocks.end()) return nullptr;
+        void *p = it->second;
+        blocks.erase(it);
+        held -= bytes;
+        return p;
+    }
+    bool put(int dev, void *p, size_t bytes) {
+        std::lock_guard<std::mutex> l(mu);
+        if (held + bytes > kCap) return false;
+        blocks.insert({{dev, bytes}, p});
+        held += bytes;
+        return true;
+    }
+};
+static DevCache g_dev_cache;
 
 // ---- host <-> device staging for pageable caller memory (the reference's struct coef buffers are
 // malloc-family memory): 8 MB pinned chunks, double buffered, the pageable side copied by the
@@ -136,13 +158,28 @@ struct j2p_session {
     unsigned long long next_log_iter = 0;
     cudaEvent_t ev[kEventRing] = {};
     long long ev_iter[kEventRing];
+    std::vector<std::pair<void *, size_t>> dev_blocks;   // everything this session took from the device cache
     void *stage[kStageSlots] = {};            // pinned staging ring (lazily taken from the process-wide pool)
     cudaEvent_t stage_ev[kStageSlots] = {};
     unsigned stage_next = 0;
 };
 
+template <typename T>
+static cudaError_t dev_alloc(j2p_session *s, T **p, size_t bytes) {
+    bytes = bytes ? (bytes + 255) & ~(size_t)255 : 256;
+    void *q = g_dev_cache.get(s->device, bytes);
+    if (!q) {
+        const cudaError_t e = cudaMalloc(&q, bytes);
+        if (e != cudaSuccess) return e;
+    }
+    s->dev_blocks.push_back({q, bytes});
+    *p = reinterpret_cast<T *>(q);
+    return cudaSuccess;
+}
+
 static std::once_flag g_cfg_once[64];
 static cudaError_t g_cfg_err[64];
+static int g_cfg_cc[64];
 
 extern "C" const char *j2p_last_error(void) { return g_err; }
 
@@ -167,13 +204,8 @@ extern "C" void j2p_session_destroy(j2p_session *s) {
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    for (int c = 0; c < 3; c++) {
-        dev_free(s->x[c], s->stream); dev_free(s->xp[c], s->stream); dev_free(s->g[c], s->stream); dev_free(s->gp[c], s->stream);
-        dev_free(s->fdata0[c], s->stream); dev_free(s->data[c], s->stream);
-    }
-    dev_free(s->F.partials, s->stream); dev_free(s->F.norms, s->stream); dev_free(s->F.counter, s->stream);
-    dev_free(s->F.sums, s->stream); dev_free(s->F.logsums, s->stream);
-    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (auto &blk : s->dev_blocks)                   // the stream is idle: nothing uses the blocks any more
+        if (!g_dev_cache.put(s->device, blk.first, blk.second)) cudaFree(blk.first);
     for (int i = 0; i < kEventRing; i++)
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     for (int k = 0; k < kStageSlots; k++) {          // the stream is idle: no DMA touches the ring any more
@@ -193,22 +225,17 @@ static int create_impl(j2p_session *s, int device, const j2p_frame_desc *d, unsi
     s->device = device;
     s->desc = *d;
     CK(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) return fail(J2P_ERR_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
-    if (device < 64) {
-        std::call_once(g_cfg_once[device], [&] {
-            g_cfg_err[device] = configure_kernels();
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-                unsigned long long keep = ~0ull;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-            }
-        });
-        CK(g_cfg_err[device]);
-    } else {
-        CK(configure_kernels());
-    }
+    if (device >= 64) return fail(J2P_ERR_ARG, "device ordinal %d not supported", device);
+    std::call_once(g_cfg_once[device], [&] {            // once per device and process: these queries are slow
+        int major = 0, minor = 0;
+        cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device);
+        g_cfg_cc[device] = major * 10 + minor;
+        g_cfg_err[device] = e != cudaSuccess ? e : (major >= 10 ? configure_kernels() : cudaSuccess);
+    });
+    if (g_cfg_cc[device] < 100)
+        return fail(J2P_ERR_NODEVICE, "device %d is sm_%d; this library is built for sm_100a only", device, g_cfg_cc[device]);
+    CK(g_cfg_err[device]);
 
     FrameDev &F = s->F;
     F.nc = (int)d->nchannel;
@@ -269,23 +296,23 @@ static int create_impl(j2p_session *s, int device, const j2p_frame_desc *d, unsi
         P.p_alpha = d->pweight[c] * 2 * 255 * sqrtf(2);                 // compute.c:245
         P.cnt = (float)(d->w_samp[c] * d->h_samp[c]);                   // compute.c:359
         const size_t nc = (size_t)P.cw * P.ch;
-        CK(dev_alloc(&s->x[c], n * sizeof(float), s->stream));
-        CK(dev_alloc(&s->xp[c], n * sizeof(float), s->stream));
-        CK(dev_alloc(&s->g[c], n * sizeof(float), s->stream));
-        CK(dev_alloc(&s->gp[c], nc * sizeof(float), s->stream));
-        CK(dev_alloc(&s->fdata0[c], nc * sizeof(float), s->stream));
-        CK(dev_alloc(&s->data[c], nc * sizeof(int16_t), s->stream));
+        CK(dev_alloc(s, &s->x[c], n * sizeof(float)));
+        CK(dev_alloc(s, &s->xp[c], n * sizeof(float)));
+        CK(dev_alloc(s, &s->g[c], n * sizeof(float)));
+        CK(dev_alloc(s, &s->gp[c], nc * sizeof(float)));
+        CK(dev_alloc(s, &s->fdata0[c], nc * sizeof(float)));
+        CK(dev_alloc(s, &s->data[c], nc * sizeof(int16_t)));
         P.x = s->x[c]; P.xp = s->xp[c]; P.g = s->g[c]; P.gp = s->gp[c]; P.data = s->data[c];
     }
     F.grad_ctas = grad_cta_count(F.W, F.t1 - F.t0);
-    CK(dev_alloc(&F.partials, sizeof(double) * 5 * (size_t)F.grad_ctas, s->stream));
-    CK(dev_alloc(&F.norms, sizeof(float) * 8, s->stream));
-    CK(dev_alloc(&F.sums, sizeof(double) * 4, s->stream));
-    CK(dev_alloc(&F.logsums, sizeof(double) * 8, s->stream));
+    CK(dev_alloc(s, &F.partials, sizeof(double) * 5 * (size_t)F.grad_ctas));
+    CK(dev_alloc(s, &F.norms, sizeof(float) * 8));
+    CK(dev_alloc(s, &F.sums, sizeof(double) * 4));
+    CK(dev_alloc(s, &F.logsums, sizeof(double) * 8));
     CK(cudaMemsetAsync(F.logsums, 0, sizeof(double) * 8, s->stream));
     F.log_on = 0;
     F.log_slot = 0;
-    CK(dev_alloc(&F.counter, sizeof(unsigned), s->stream));
+    CK(dev_alloc(s, &F.counter, sizeof(unsigned)));
     CK(cudaMemsetAsync(F.counter, 0, sizeof(unsigned), s->stream));
     CK(cudaMemsetAsync(F.norms, 0, sizeof(float) * 8, s->stream));
     return J2P_OK;

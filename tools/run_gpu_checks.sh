@@ -1,15 +1,15 @@
 #!/bin/bash
-# round-end evidence run on one GPU: GPU tests, e2e phase trace, bench + ncu captures
+# round-end evidence run on one GPU: GPU tests, e2e phase trace, bench (+ its traced twin), ncu captures
 mkdir -p gpurun_out
-TAG=${1:-r01c}
+TAG=${1:-r01e}
 timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1
 tail -3 gpurun_out/pytest_gpu.log
-timeout 200 python tools/e2e_trace.py 2>&1 | grep -v "^$" | tail -14 > gpurun_out/e2e_trace_${TAG}.log
-cat gpurun_out/e2e_trace_${TAG}.log
 export J2P_EXPECT_GPU=1
 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err
-tail -c 2600 gpurun_out/bench_${TAG}.json
-tail -5 gpurun_out/bench_${TAG}.err
+tail -c 2700 gpurun_out/bench_${TAG}.json
+tail -3 gpurun_out/bench_${TAG}.err
+J2P_TRACE=1 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_trace.json 2> gpurun_out/bench_trace.err
+grep "j2p trace: \(create\|upload\|queue\|device\|download\|destroy\)" gpurun_out/bench_trace.err | tail -12
 ncu --metrics gpu__time_duration.sum --clock-control none -s 12 -c 32 --csv --log-file gpurun_out/launches_${TAG}.csv python tools/prof_driver.py > gpurun_out/ncu_list_${TAG}.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_gradient -s 4 -c 1 -o gpurun_out/prof_gradient_${TAG} -f python tools/prof_driver.py > gpurun_out/ncu_grad_${TAG}.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_project -s 4 -c 1 -o gpurun_out/prof_project_${TAG} -f python tools/prof_driver.py > gpurun_out/ncu_proj_${TAG}.log 2>&1
