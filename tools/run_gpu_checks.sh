@@ -1,16 +1,9 @@
 #!/bin/bash
-# round-end evidence run on one GPU: GPU tests, e2e phase trace, bench (+ its traced twin), ncu captures
+# 2 GPUs: strip parity (both drivers) with the final kernels, strong scaling N=2, bench N=2 under torchrun
 mkdir -p gpurun_out
-TAG=${1:-r01e}
-timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1
-tail -3 gpurun_out/pytest_gpu.log
-export J2P_EXPECT_GPU=1
-python bench.py --steps 5 --warmup 3 > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err
-tail -c 2700 gpurun_out/bench_${TAG}.json
-tail -3 gpurun_out/bench_${TAG}.err
-J2P_TRACE=1 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_trace.json 2> gpurun_out/bench_trace.err
-grep "j2p trace: \(create\|upload\|queue\|device\|download\|destroy\)" gpurun_out/bench_trace.err | tail -12
-ncu --metrics gpu__time_duration.sum --clock-control none -s 12 -c 32 --csv --log-file gpurun_out/launches_${TAG}.csv python tools/prof_driver.py > gpurun_out/ncu_list_${TAG}.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_gradient -s 4 -c 1 -o gpurun_out/prof_gradient_${TAG} -f python tools/prof_driver.py > gpurun_out/ncu_grad_${TAG}.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_project -s 4 -c 1 -o gpurun_out/prof_project_${TAG} -f python tools/prof_driver.py > gpurun_out/ncu_proj_${TAG}.log 2>&1
-tail -2 gpurun_out/ncu_proj_${TAG}.log
+timeout 600 python -m pytest tests/test_gpu_strips.py -m gpu -q -x > gpurun_out/strips.log 2>&1
+echo "pytest exit $?" >> gpurun_out/strips.log
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/strip_bench.py >> gpurun_out/strips.log 2> gpurun_out/strips_err_2.log
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
+grep -v "^$" gpurun_out/strips.log | tail -12
+python -c "import json;d=json.loads(open('gpurun_out/bench_n2.json').read().strip().splitlines()[-1]);print('N=2 value', d['value'], 'e2e', d['e2e']['value'], d['e2e']['ms_per_step'])"
