@@ -7,14 +7,9 @@
 #include "numerics.cuh"
 #include "project_common.cuh"
 
-#ifndef J2P_EXP
-#define J2P_EXP 0      // measurement aid (tools/): bit mask of phases to knock out in k_project<>; 0 in every real build
-#endif
 
 namespace j2p {
 
-cudaError_t configure_project_blk();
-cudaError_t launch_project_blk(const FrameDev &F, int c, float factor, cudaStream_t s);
 cudaError_t launch_project_tile(const FrameDev &F, int c, int count, float factor, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------
@@ -120,13 +115,6 @@ __global__ void __launch_bounds__(P_NT, (SW * SH <= 1) ? J2P_PROJ_MIN_CTAS : 2) 
                 } else {
                     a = xr[k]; p = pr[k]; g = gr[k];
                 }
-                if (J2P_EXP & 8) {
-                    z[sy][k * 4 + 0] = fadd(a.x, fadd(p.x, g.x));
-                    z[sy][k * 4 + 1] = fadd(a.y, fadd(p.y, g.y));
-                    z[sy][k * 4 + 2] = fadd(a.z, fadd(p.z, g.z));
-                    z[sy][k * 4 + 3] = fadd(a.w, fadd(p.w, g.w));
-                    continue;
-                }
                 z[sy][k * 4 + 0] = stepper.fast(a.x, p.x, g.x, key);
                 z[sy][k * 4 + 1] = stepper.fast(a.y, p.y, g.y, key);
                 z[sy][k * 4 + 2] = stepper.fast(a.z, p.z, g.z, key);
@@ -181,7 +169,7 @@ __global__ void __launch_bounds__(P_NT, (SW * SH <= 1) ? J2P_PROJ_MIN_CTAS : 2) 
         }
     }
 
-    if (!(J2P_EXP & 1)) fdct8x8_rows(v, tileA, j);
+    fdct8x8_rows(v, tileA, j);
 
     // ---- clamp to the quantisation interval (compute.c:323-331); DCT-distance residual ---------
     const int dw[4] = {draw.x, draw.y, draw.z, draw.w};
@@ -200,10 +188,6 @@ __global__ void __launch_bounds__(P_NT, (SW * SH <= 1) ? J2P_PROJ_MIN_CTAS : 2) 
     }
     float r[8], num[8];
     unsigned rkey = 0xffffffffu;
-    if (J2P_EXP & 2) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) { num[i] = 0.f; r[i] = fadd(v[i], qv[i] + (float)dw[i & 3]); }
-    } else {
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         const int di = (i & 1) ? (dw[i >> 1] >> 16) : (int)(short)(dw[i >> 1] & 0xffff);
@@ -232,15 +216,12 @@ __global__ void __launch_bounds__(P_NT, (SW * SH <= 1) ? J2P_PROJ_MIN_CTAS : 2) 
         loc = __dadd_rn(loc, __shfl_xor_sync(gmask, loc, 4));
         if (j == 0) atomicAdd(&F.logsums[2 + 3 * F.log_slot + c], loc);
     }
-    }
 
-    if (J2P_EXP & 4) {
-    } else if (P.use_prob) {
+    if (P.use_prob) {
         idct8x8_rows_x2(v, r, tileA, tileB, j);
     } else {
         idct8x8_rows(v, tileA, j);
     }
-    if ((J2P_EXP & 16) && v[0] != 123.456f) return;
     if (P.use_prob) {
         float4 *gprow = reinterpret_cast<float4 *>(P.gp + (size_t)cy * P.cw + bx * 8);
         const float pa = P.p_alpha;                                          // compute.c:62 (the product)
@@ -327,221 +308,9 @@ __global__ void k_init_plane(const float *fdata, float *x, float *xp, int W, int
 }
 
 // ------------------------------------------------------------------------------------------
-// k_project_pipe — the full-resolution (1x1) plane, persistent and software-pipelined.
-//
-// Same arithmetic as k_project<1,1>.  What changes is the schedule: the transforms are bound by
-// the XU pipe (fp64 conversions, 16 per clock and SM; profiles/r01_microbench2.txt shows the
-// three transforms of a block sustain the XU limit when they run back to back), so XU must
-// never idle while a CTA waits for HBM or steps/clamps/stores.  Each CTA therefore loops over
-// tiles; every thread copies the 112 bytes it will need for the NEXT tile (its own row of x_k,
-// x_{k-1}, g and its coefficient row) into a private shared-memory slot with cp.async while it
-// works on the current one.  The slots are thread-private, so the loop has no block barrier and
-// the warps of an SM drift into different phases, which keeps all pipes busy.
-// ------------------------------------------------------------------------------------------
-constexpr int PP_SLOTS = 7;   // x lo/hi, xp lo/hi, g lo/hi, coefficient row
-constexpr size_t PP_DYN_SMEM = 2u * PP_SLOTS * P_NT * sizeof(float4);
-
-__global__ void __launch_bounds__(P_NT, 3) k_project_pipe(const __grid_constant__ FrameDev F, const ProjPlane G, const float factor,
-                                                           const int ntiles) {
-    extern __shared__ __align__(16) float4 stage[];              // [2][PP_SLOTS][P_NT]
-    __shared__ __align__(16) float tiles[P_NT / 8][TILE_STRIDE];
-    __shared__ __align__(16) float sq[3][64];
-    __shared__ float snorm[2];
-    const int tid = threadIdx.x;
-    const int c = G.c;
-    const PlaneDev &P = F.pl[c];
-    const int W = F.W, H = F.H;
-    const int b = tid >> 3, j = tid & 7;
-    const int bw = P.cw >> 3, bh = P.ch >> 3;
-
-    auto tile_block = [&](int t, int &bx, int &by) {
-        const int ctay = t / G.gx, ctax = t - ctay * G.gx;
-        bx = ctax * P_BW + (b & (P_BW - 1));
-        by = ctay * P_BH + (b >> J2P_PBW_LOG2);
-    };
-    auto issue = [&](int t, int st) {
-        int bx, by;
-        tile_block(t, bx, by);
-        if (bx < bw && by < bh) {
-            float4 *slot = stage + (size_t)st * PP_SLOTS * P_NT + tid;
-            const size_t gi = (size_t)(by * 8 + j) * W + (size_t)bx * 8;
-            cp_async16(slot + 0 * P_NT, P.x + gi);
-            cp_async16(slot + 1 * P_NT, P.x + gi + 4);
-            cp_async16(slot + 2 * P_NT, P.xp + gi);
-            cp_async16(slot + 3 * P_NT, P.xp + gi + 4);
-            cp_async16(slot + 4 * P_NT, P.g + gi);
-            cp_async16(slot + 5 * P_NT, P.g + gi + 4);
-            cp_async16(slot + 6 * P_NT, P.data + ((size_t)(by * bw + bx) * 64 + j * 8));
-        }
-        cp_async_commit();
-    };
-
-    int t = blockIdx.x;
-    if (t < ntiles) issue(t, 0);
-    if (tid < 64) {
-        sq[0][tid] = F.q[c][tid];
-        sq[1][tid] = F.qq[c][tid];
-        sq[2][tid] = F.rqq[c][tid];
-    } else if (tid == 64) {
-        snorm[0] = F.norms[c];
-        snorm[1] = F.norms[4 + c];
-    }
-    __syncthreads();
-    Stepper stepper;
-    stepper.factor = factor;
-    stepper.step = F.step;
-    stepper.norm = snorm[0];
-    stepper.rn = snorm[1];
-    stepper.stepping = stepper.norm != 0.f;                        // compute.c:211
-    const bool norm_ok = qdiv_divisor_ok(stepper.norm);
-    float *tile = tiles[b];
-    const unsigned gmask = 0xffu << (tid & 24);               // the 8 lanes that own this block
-    // this thread's rows of the three tables (constant over the tile loop)
-    float qv[8], qqv[8], rqv[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        qv[k] = sq[0][j * 8 + k];
-        qqv[k] = sq[1][j * 8 + k];
-        rqv[k] = sq[2][j * 8 + k];
-    }
-    const float pa = P.p_alpha;
-    const bool use_prob = P.use_prob != 0, resample = P.resample != 0;
-
-    for (int n = 0; t < ntiles; n++) {
-        const int tnext = t + gridDim.x;
-        if (tnext < ntiles) issue(tnext, (n + 1) & 1);
-        else cp_async_commit();
-        cp_async_wait<1>();                                        // the copies of tile t (this thread's own) have landed
-
-        int bx, by;
-        tile_block(t, bx, by);
-        t = tnext;
-        const int cy = by * 8 + j;
-        if (!(bx < bw && by < bh)) {
-            // pixels of the frame that no coefficient block covers: step only (compute.c:349-350 never visits them)
-            for (int i = 0; i < 8; i++) {
-                const int px = bx * 8 + i;
-                if (px < W && cy < H) {
-                    const size_t gi = (size_t)cy * W + px;
-                    P.xp[gi] = stepper(P.x[gi], P.xp[gi], P.g[gi]);
-                }
-            }
-            continue;      // whole 8-lane groups skip together; the warp barriers below are per 8-lane group
-        }
-        const float4 *slot = stage + (size_t)(n & 1) * PP_SLOTS * P_NT + tid;
-        float z[8];
-        {
-            unsigned key = 0xffffffffu;
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                const float4 a = slot[(0 + k) * P_NT], p = slot[(2 + k) * P_NT], g = slot[(4 + k) * P_NT];
-                z[k * 4 + 0] = stepper.fast(a.x, p.x, g.x, key);
-                z[k * 4 + 1] = stepper.fast(a.y, p.y, g.y, key);
-                z[k * 4 + 2] = stepper.fast(a.z, p.z, g.z, key);
-                z[k * 4 + 3] = stepper.fast(a.w, p.w, g.w, key);
-            }
-            if (stepper.stepping && !(norm_ok && key >= QDIV_KEY_MIN)) {   // outside the proven range: IEEE division
-#pragma unroll
-                for (int k = 0; k < 2; k++) {
-                    const float4 a = slot[(0 + k) * P_NT], p = slot[(2 + k) * P_NT], g = slot[(4 + k) * P_NT];
-                    z[k * 4 + 0] = stepper(a.x, p.x, g.x);
-                    z[k * 4 + 1] = stepper(a.y, p.y, g.y);
-                    z[k * 4 + 2] = stepper(a.z, p.z, g.z);
-                    z[k * 4 + 3] = stepper(a.w, p.w, g.w);
-                }
-            }
-        }
-        const float4 dq = slot[6 * P_NT];
-        const int dw[4] = {__float_as_int(dq.x), __float_as_int(dq.y), __float_as_int(dq.z), __float_as_int(dq.w)};
-
-        float v[8], mean[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            if (resample) {                                        // sampling 1x1 but a coefficient grid smaller than the frame
-                const float m = fmul(fadd(0.f, z[i]), 1.0f);      // compute.c:351-359 with one sample: (0 + z) / 1
-                mean[i] = m;
-                v[i] = m;
-            } else {
-                mean[i] = 0.f;
-                v[i] = z[i];
-            }
-        }
-
-        fdct8x8_rows(v, tile, j, gmask);
-
-        // clamp to the quantisation interval (compute.c:323-331); DCT-distance residual (compute.c:47-49)
-        float r[8], num[8];
-        unsigned rkey = 0xffffffffu;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int di = (i & 1) ? (dw[i >> 1] >> 16) : (int)(short)(dw[i >> 1] & 0xffff);
-            const float d = (float)di;
-            const float q = qv[i];
-            const float lo = fmul(fsub(d, 0.5f), q), hi = fmul(fadd(d, 0.5f), q);
-            float tv = v[i];
-            tv = tv > hi ? hi : (tv < lo ? lo : tv);
-            v[i] = tv;
-            num[i] = fsub(tv, fmul(d, q));
-            rkey = min(rkey, qdiv_key(num[i]));
-            r[i] = qdiv_core(num[i], qqv[i], rqv[i]);
-        }
-        if (rkey < QDIV_KEY_MIN) {
-#pragma unroll
-            for (int i = 0; i < 8; i++) r[i] = fdiv(num[i], qqv[i]);
-        }
-
-        idct8x8_rows(v, tile, j, gmask);
-        if (use_prob) {
-            idct8x8_rows(r, tile, j, gmask);
-            float4 *gprow = reinterpret_cast<float4 *>(P.gp + (size_t)cy * P.cw + bx * 8);
-            gprow[0] = make_float4(fmul(pa, r[0]), fmul(pa, r[1]), fmul(pa, r[2]), fmul(pa, r[3]));   // compute.c:62 (the product)
-            gprow[1] = make_float4(fmul(pa, r[4]), fmul(pa, r[5]), fmul(pa, r[6]), fmul(pa, r[7]));
-        }
-
-        // write x_{k+1} over x_{k-1} (compute.c:387-403)
-        float4 *o = reinterpret_cast<float4 *>(P.xp + (size_t)cy * W + (size_t)bx * 8);
-        if (resample) {
-            float e[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) e[i] = fadd(fsub(z[i], mean[i]), v[i]);
-            o[0] = make_float4(e[0], e[1], e[2], e[3]);
-            o[1] = make_float4(e[4], e[5], e[6], e[7]);
-        } else {
-            o[0] = make_float4(v[0], v[1], v[2], v[3]);
-            o[1] = make_float4(v[4], v[5], v[6], v[7]);
-        }
-    }
-    cp_async_wait<0>();
-}
-
-// ------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------
-static int g_pipe_slots = 148 * 3;   // resident CTAs of k_project_pipe on the whole device
-// Which organisation projects a full-resolution plane:
-//   0 = 8 threads per block, coalesced swizzled staging (kernels_project_tile.cu)   [default]
-//   1 = 8 threads per block, persistent, thread-private cp.async staging
-//   2 = 8 threads per block, each thread fetches its own row
-//   3 = one thread per block, registers only (kernels_project_blk.cu)
-// J2P_PROJ_VARIANT is a measurement aid for profiles/; all four are bit-identical.
-static int g_proj_variant = 0;
-
-cudaError_t configure_project_kernels() {
-    if (const char *v = getenv("J2P_PROJ_VARIANT")) g_proj_variant = atoi(v);
-    cudaError_t e = configure_project_blk();
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_project_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PP_DYN_SMEM);
-    if (e != cudaSuccess) return e;
-    int per_sm = 0, dev = 0, sms = 0;
-    e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_project_pipe, P_NT, PP_DYN_SMEM);
-    if (e != cudaSuccess) return e;
-    g_pipe_slots = sms * (per_sm > 0 ? per_sm : 1);
-    return cudaSuccess;
-}
+cudaError_t configure_project_kernels() { return cudaSuccess; }   // nothing to opt into: static shared memory only
 
 // strip sessions: fold the per-rank sums of g^2 in rank order (deterministic), then the norms of
 // compute.c:200-206 and their reciprocals
@@ -581,7 +350,7 @@ cudaError_t launch_project(const FrameDev &Fin, float factor, cudaStream_t s) {
         const dim3 grid(G.gx, (F.H + th - 1) / th);
         if (F.log_on && P.sw == 1 && P.sh == 1) {
             k_project<1, 1><<<grid, P_NT, 0, s>>>(F, G, factor);                // the variant that also sums the log terms
-        } else if (P.sw == 1 && P.sh == 1 && g_proj_variant == 0) {
+        } else if (P.sw == 1 && P.sh == 1) {
             int count = 1;      // following planes of identical geometry ride in the same launch (grid.z)
             while (c + count < F.nc && F.pl[c + count].sw == 1 && F.pl[c + count].sh == 1 && F.pl[c + count].cw == P.cw &&
                    F.pl[c + count].ch == P.ch)
@@ -589,15 +358,6 @@ cudaError_t launch_project(const FrameDev &Fin, float factor, cudaStream_t s) {
             const cudaError_t eb = launch_project_tile(F, c, count, factor, s);
             if (eb != cudaSuccess) return eb;
             c += count - 1;
-        } else if (P.sw == 1 && P.sh == 1 && g_proj_variant == 3) {
-            const cudaError_t eb = launch_project_blk(F, c, factor, s);
-            if (eb != cudaSuccess) return eb;
-        } else if (P.sw == 1 && P.sh == 1 && g_proj_variant == 1) {
-            const int ntiles = (int)(grid.x * grid.y);
-            const int ctas = ntiles < g_pipe_slots ? ntiles : g_pipe_slots;
-            k_project_pipe<<<ctas, P_NT, PP_DYN_SMEM, s>>>(F, G, factor, ntiles);
-        } else if (P.sw == 1 && P.sh == 1) {
-            k_project<1, 1><<<grid, P_NT, 0, s>>>(F, G, factor);
         }
         else if (P.sw == 2 && P.sh == 2) k_project<2, 2><<<grid, P_NT, 0, s>>>(F, G, factor);
         else if (P.sw == 2 && P.sh == 1) k_project<2, 1><<<grid, P_NT, 0, s>>>(F, G, factor);

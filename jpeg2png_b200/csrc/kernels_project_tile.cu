@@ -191,7 +191,43 @@ __global__ void __launch_bounds__(PT_NT, J2P_TILE_MIN_CTAS) k_project_tile(const
     }
 }
 
-cudaError_t launch_step_uncovered(const FrameDev &F, int c, float factor, cudaStream_t s);
+// Frame pixels of a 1x1 plane that no coefficient block covers (1080p: luma rows 1080..1087) are
+// only stepped: compute_projection never visits them (compute.c:349-350).  The region is the
+// bottom band (rows >= ch, full width) plus the right band (rows < ch, columns >= cw).
+__global__ void k_step_uncovered(const __grid_constant__ FrameDev F, const int c, const float factor) {
+    const PlaneDev &P = F.pl[c];
+    const int W = F.W, H = F.H;
+    Stepper stepper;
+    stepper.factor = factor;
+    stepper.step = F.step;
+    stepper.norm = F.norms[c];
+    stepper.rn = 0.f;
+    stepper.stepping = stepper.norm != 0.f;
+    const unsigned bottom = (unsigned)(H - P.ch) * (unsigned)W, right_w = (unsigned)(W - P.cw);
+    const unsigned n = bottom + (unsigned)P.ch * right_w;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        unsigned px, py;
+        if (i < bottom) {
+            py = (unsigned)P.ch + i / (unsigned)W;
+            px = i % (unsigned)W;
+        } else {
+            const unsigned k = i - bottom;
+            py = k / right_w;
+            px = (unsigned)P.cw + k % right_w;
+        }
+        const size_t gi = (size_t)py * W + px;
+        P.xp[gi] = stepper(P.x[gi], P.xp[gi], P.g[gi]);
+    }
+}
+
+static cudaError_t launch_step_uncovered(const FrameDev &F, int c, float factor, cudaStream_t s) {
+    const PlaneDev &P = F.pl[c];
+    const size_t n = (size_t)(F.H - P.ch) * F.W + (size_t)P.ch * (F.W - P.cw);
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_step_uncovered<<<blocks, 256, 0, s>>>(F, c, factor);
+    return cudaGetLastError();
+}
 
 // F: already restricted to the rows the session owns (launch_project).  Projects planes
 // c .. c+count-1, which must all be 1x1 planes with the same coefficient grid.
