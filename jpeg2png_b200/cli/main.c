@@ -22,6 +22,7 @@
 #include <string.h>
 #ifdef _OPENMP
 #include <omp.h>
+#include <time.h>
 #endif
 
 #include "../../include/jpeg2png_b200.h"
@@ -149,7 +150,16 @@ static void solve(const struct j2p_jpeg *jpeg, const unsigned *chan, unsigned nc
         j2p_session_destroy(s);
 }
 
+static double now_ms(void) {
+        struct timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 static void decode_file(const char *infile, const char *outfile, const struct job *job, int device, struct progressbar *pb) {
+        const char *tr = getenv("J2P_TRACE");
+        const int trace = tr && *tr == '1';
+        const double t_begin = trace ? now_ms() : 0;
         FILE *in = fopen(infile, "rb");
         if (!in) { if (main_pb) { pb_clear(); main_pb = NULL; } fprintf(stderr, "jpeg2png: could not open input file `%s`: ", infile); perror(NULL); exit(EXIT_FAILURE); }
         fseek(in, 0, SEEK_END);
@@ -163,6 +173,7 @@ static void decode_file(const char *infile, const char *outfile, const struct jo
         if (j2p_read_jpeg_mem(buf, (size_t)len, &jpeg, err, sizeof err) != 0) die("%s", err);
         free(buf);
 
+        const double t_read = trace ? now_ms() : 0;
         float *planes[3] = {NULL, NULL, NULL};
         unsigned pw[3], ph[3];
         if (job->all_together) {                                                 /* jpeg2png.c:142-144 */
@@ -174,12 +185,16 @@ static void decode_file(const char *infile, const char *outfile, const struct jo
                 for (unsigned i = 0; i < 3; i++) solve(&jpeg, &i, 1, device, job, job->iterations[i], job->weights[i], pb, infile, i, &planes[i], &pw[i], &ph[i]);
         }
         for (size_t i = 0; i < (size_t)pw[0] * ph[0]; i++) planes[0][i] += 128.f;   /* jpeg2png.c:156-159 */
+        const double t_solve = trace ? now_ms() : 0;
 
         FILE *out = fopen(outfile, "wb");
         if (!out) { if (main_pb) { pb_clear(); main_pb = NULL; } fprintf(stderr, "jpeg2png: could not open output file `%s`: ", outfile); perror(NULL); exit(EXIT_FAILURE); }
         if (j2p_write_png(out, jpeg.w, jpeg.h, job->png_bits, planes[0], pw[0], planes[1], pw[1], planes[2], pw[2]) != 0) die("could not write PNG file `%s`", outfile);
         fclose(out);
         for (int i = 0; i < 3; i++) { free(planes[i]); free(jpeg.coefs[i].data); }
+        if (trace)
+                fprintf(stderr, "j2p trace: %s: read+parse %.1f ms, solve (upload..download) %.1f ms, colour+PNG %.1f ms (thread %d, started at %.1f)\n", infile,
+                        t_read - t_begin, t_solve - t_read, now_ms() - t_solve, omp_get_thread_num(), t_begin);
 }
 
 /* ---- option parsing -------------------------------------------------------------------------- */

@@ -25,8 +25,10 @@ with tempfile.TemporaryDirectory() as d:
                 os.remove(png)
         cmd = [exe, '-q', '-i', '100'] + (['-t', threads] if threads else []) + files
         t0 = time.perf_counter()
-        r = subprocess.run(cmd, capture_output=True, text=True)
+        r = subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ, J2P_TRACE='1') if rep == 1 else None)
         dt = time.perf_counter() - t0
         assert r.returncode == 0, r.stderr
         print(f'cli batch: {n} x 1920x1080 Q75 4:2:0, -i 100{" -t " + threads if threads else ""}: {dt:.2f} s  '
               f'{n / dt:.1f} files/s  {n * 1920 * 1080 * 100 / dt / 1e6:.0f} Mpix-it/s (JPEG read + solve + PNG write)', flush=True)
+        if rep == 1:
+            print('\n'.join(l for l in r.stderr.splitlines() if 'read+parse' in l)[:4000], flush=True)
