@@ -56,8 +56,10 @@ struct progressbar;
 /* ---------------------------------------------------------------------------------------
  * 1. Drop-in entry.  Replaces reference compute.c:407-465.
  *
- *   - frees coefs[c].fdata (it must come from aligned_alloc/malloc, utils.h:89-106) and replaces
- *     it with a new 16-byte-aligned malloc-family buffer of H*W floats owned by the caller;
+ *   - consumes coefs[c].fdata (it must come from aligned_alloc/malloc, utils.h:89-106) and sets
+ *     it to a 16-byte-aligned malloc-family buffer of H*W floats owned by the caller — the
+ *     consumed buffer itself when the plane already has frame size, a new one (and the old one
+ *     freed, compute.c:304-305, :458) otherwise;
  *   - overwrites coefs[c].w/h with the frame size W,H (compute.c:460-461);
  *   - re-entrant: may be called concurrently from several host threads (jpeg2png.c:147, :330);
  *     each call uses its own CUDA stream and no mutable global state;
@@ -145,6 +147,14 @@ int j2p_comm_unique_id(void *out, size_t bytes);
 int j2p_comm_create(j2p_comm **out, int device, int nranks, int rank, const void *id, size_t bytes);
 void j2p_comm_destroy(j2p_comm *c);
 int j2p_session_iterate_strip(j2p_session *s, j2p_comm *c, unsigned n);
+/* 0, or an error if a peer-memory exchange timed out on the device.  Only the opt-in peer-memory
+ * protocol can fail this way (environment J2P_STRIP_P2P=1: the ranks store the sums and the border
+ * rows straight into each other's memory over NVLink, cudaIpc mappings, instead of calling NCCL
+ * inside the loop; same results).  Synchronises the device.  Destroy the communicator before the
+ * session it was used with. */
+int j2p_comm_status(j2p_comm *c);
+/* 1 if j2p_session_iterate_strip exchanges through peer memory, 0 if through NCCL. */
+int j2p_comm_protocol(const j2p_comm *c);
 
 /* Working-frame size W x H = max over planes of (plane_w*w_samp, plane_h*h_samp) (compute.c:410-416). */
 unsigned j2p_session_width(const j2p_session *s);

@@ -145,6 +145,10 @@ def declare_product(lib: C.CDLL) -> C.CDLL:
     lib.j2p_comm_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, vp, C.c_size_t]
     lib.j2p_comm_destroy.restype = None
     lib.j2p_comm_destroy.argtypes = [vp]
+    lib.j2p_comm_protocol.restype = C.c_int
+    lib.j2p_comm_protocol.argtypes = [vp]
+    lib.j2p_comm_status.restype = C.c_int
+    lib.j2p_comm_status.argtypes = [vp]
     lib.j2p_session_iterate_strip.restype = C.c_int
     lib.j2p_session_iterate_strip.argtypes = [vp, vp, C.c_uint]
     lib.j2p_session_destroy.restype = None
@@ -187,7 +191,7 @@ HEADER_SYMBOLS = [
     'compute', 'j2p_last_error', 'j2p_device_count', 'j2p_session_create', 'j2p_session_destroy',
     'j2p_session_create_strip', 'j2p_session_strip_info', 'j2p_session_gradient', 'j2p_session_sums_ptr',
     'j2p_session_project', 'j2p_session_halo', 'j2p_session_copy_halo_to_prev',
-    'j2p_comm_unique_id', 'j2p_comm_create', 'j2p_comm_destroy', 'j2p_session_iterate_strip',
+    'j2p_comm_unique_id', 'j2p_comm_create', 'j2p_comm_destroy', 'j2p_comm_status', 'j2p_comm_protocol', 'j2p_session_iterate_strip',
     'j2p_session_width', 'j2p_session_height', 'j2p_session_upload', 'j2p_session_reset',
     'j2p_session_iterate', 'j2p_session_profile', 'j2p_session_wait_iteration', 'j2p_session_download', 'j2p_session_set_logging',
     'j2p_session_objective', 'j2p_session_sync', 'j2p_session_stream', 'j2p_session_plane_ptr',

@@ -46,4 +46,22 @@ struct FrameDev {
     double *logsums;      // [0]=tv, [1]=tv2, [2+3*slot+c] = sum over plane c of (residual/q)^2
 };
 
+// ---- strip exchanges over peer memory (kernels_strip.cu); pointers into OTHER ranks' memory are
+// cudaIpc mappings made by session.cu
+struct StripPeers {
+    double *mail[8];          // rank p's mailbox base, as mapped here: [2 slots][nranks][4] doubles
+    unsigned *mail_flag[8];   // rank p's mailbox flags: [2 slots][nranks]
+    int nranks, rank;
+};
+struct HaloPeers {
+    float *up_dst[3];         // where this strip's first two rows go: the upper neighbour's bottom halo rows, per plane
+    float *down_dst[3];       // where the last two rows go: the lower neighbour's top halo rows
+    const float *up_src[3];   // this strip's first two owned rows
+    const float *down_src[3]; // this strip's last two owned rows
+    unsigned *up_flag, *down_flag;         // the neighbours' words for "my lower / upper neighbour has delivered"
+    const unsigned *from_up, *from_down;   // this rank's own words
+    int has_up, has_down, nc;
+    unsigned n4;              // float4s per plane and side: 2 rows * W / 4
+};
+
 }  // namespace j2p

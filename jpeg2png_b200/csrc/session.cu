@@ -40,6 +40,10 @@ cudaError_t launch_fold_sums(const double *sums_by_rank, int nranks, int nc, flo
 cudaError_t launch_decode(const int16_t *data, const float *q_host, float *out, int cw, int ch, cudaStream_t s);
 cudaError_t launch_init_plane(const float *fdata, float *x, float *xp, int W, int H, int cw, int ch, int sw, int sh,
                               cudaStream_t s);
+// kernels_strip.cu: the strip exchanges over peer memory (parameter blocks in kernels.cuh)
+cudaError_t launch_sums_exchange(const StripPeers &P, const double *my_sums, double *my_mail, unsigned *my_flag, unsigned seq, int nc,
+                                 float *norms, int *err, cudaStream_t s);
+cudaError_t launch_halo_exchange(const HaloPeers &P, unsigned seq, unsigned *ticket, int *err, cudaStream_t s);
 }  // namespace j2p
 
 using namespace j2p;
@@ -757,10 +761,27 @@ const NcclApi *nccl_api() {
 }
 }  // namespace
 
+// What a rank publishes so that the others can map its memory (cudaIpc, same node)
+struct P2PInfo {
+    cudaIpcMemHandle_t mail, flags, x[3], xp[3];
+    int t0, t1, H, W, nc, ok;
+};
+
 struct j2p_comm {
     nccl_comm_t comm = nullptr;
     int nranks = 0, rank = 0, device = 0;
     double *gathered = nullptr;                                          // [nranks][3] fp64, device
+    // ---- peer-memory binding to one session (J2P_STRIP_P2P=1; kernels_strip.cu) ----
+    j2p_session *bound = nullptr;
+    int p2p_state = 0;                                                   // 0 = not tried, 1 = bound, -1 = unavailable (NCCL path)
+    double *mail = nullptr;                                              // [2][nranks][4] doubles, written by every rank
+    unsigned *flags = nullptr;                                           // [2][nranks] mailbox flags, then from_up, from_down, ticket, err
+    std::vector<void *> opened;                                          // cudaIpcOpenMemHandle results to close again
+    StripPeers sp{};
+    float *up_buf[3][2] = {}, *down_buf[3][2] = {};                      // the neighbours' two plane buffers, mapped here
+    unsigned *up_flags = nullptr, *down_flags = nullptr;                 // the neighbours' flag blocks, mapped here
+    int up_t1 = 0, down_t0 = 0;                                          // the neighbours' owned-row bounds (their local indices)
+    unsigned seq_sums = 0, seq_halo = 0;
 };
 
 #define NK(call)                                                                                      \
@@ -806,10 +827,129 @@ extern "C" void j2p_comm_destroy(j2p_comm *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    for (void *p : c->opened) cudaIpcCloseMemHandle(p);
+    cudaFree(c->mail);
+    cudaFree(c->flags);
     const NcclApi *api = nccl_api();
     if (api && c->comm) api->CommDestroy(c->comm);
     cudaFree(c->gathered);
     delete c;
+}
+
+// 1 if the loop exchanges through peer memory, 0 if it calls NCCL (decided at the first iterate call)
+extern "C" int j2p_comm_protocol(const j2p_comm *c) { return c && c->p2p_state == 1 ? 1 : 0; }
+
+// 0 = fine; non-zero = a peer-memory wait timed out on the device (results are invalid)
+extern "C" int j2p_comm_status(j2p_comm *c) {
+    if (!c) return fail(J2P_ERR_ARG, "null communicator");
+    if (c->p2p_state != 1) return J2P_OK;
+    CK(cudaSetDevice(c->device));
+    CK(cudaDeviceSynchronize());
+    int err = 0;
+    CK(cudaMemcpy(&err, c->flags + 2 * c->nranks + 3, sizeof err, cudaMemcpyDeviceToHost));
+    if (err) return fail(J2P_ERR_CUDA, "a peer-memory exchange timed out (rank %d)", c->rank);
+    return J2P_OK;
+}
+
+// ---- peer-memory binding ------------------------------------------------------------------------
+// Collective.  Publishes this rank's mailbox, flags and plane buffers as cudaIpc handles (the plane
+// buffers are plain cudaMalloc blocks from the device cache), gathers everybody's with NCCL, maps
+// every rank's mailbox and the two neighbours' planes.  Every rank ends with the same verdict
+// (a second gather), so the loop never mixes the NCCL and the peer-memory protocol.
+static int p2p_bind(j2p_comm *c, j2p_session *s, const NcclApi *api) {
+    c->bound = s;
+    c->p2p_state = -1;
+    if (c->nranks > 8) return J2P_OK;
+    const int nr = c->nranks;
+    const FrameDev &F = s->F;
+    P2PInfo mine;
+    memset(&mine, 0, sizeof mine);
+    mine.t0 = F.t0; mine.t1 = F.t1; mine.H = F.H; mine.W = F.W; mine.nc = F.nc;
+    bool ok = cudaMalloc(&c->mail, sizeof(double) * 2 * nr * 4) == cudaSuccess &&
+              cudaMalloc(&c->flags, sizeof(unsigned) * (2 * nr + 4)) == cudaSuccess &&
+              cudaMemset(c->mail, 0, sizeof(double) * 2 * nr * 4) == cudaSuccess &&
+              cudaMemset(c->flags, 0, sizeof(unsigned) * (2 * nr + 4)) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.mail, c->mail) == cudaSuccess && cudaIpcGetMemHandle(&mine.flags, c->flags) == cudaSuccess;
+    for (int k = 0; k < F.nc && ok; k++)
+        ok = cudaIpcGetMemHandle(&mine.x[k], s->x[k]) == cudaSuccess && cudaIpcGetMemHandle(&mine.xp[k], s->xp[k]) == cudaSuccess;
+    mine.ok = ok ? 1 : 0;
+    cudaGetLastError();
+
+    // gather the descriptors (in place: my entry sits at its final position)
+    std::vector<P2PInfo> all((size_t)nr);
+    P2PInfo *d_all = nullptr;
+    CK(cudaMalloc(&d_all, sizeof(P2PInfo) * (size_t)nr));
+    CK(cudaMemcpy(d_all + c->rank, &mine, sizeof mine, cudaMemcpyHostToDevice));
+    NK(api->AllGather(d_all + c->rank, d_all, sizeof(P2PInfo), /*ncclChar*/ 0, c->comm, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    CK(cudaMemcpy(all.data(), d_all, sizeof(P2PInfo) * (size_t)nr, cudaMemcpyDeviceToHost));
+    for (int p = 0; p < nr; p++) ok = ok && all[p].ok && all[p].W == F.W && all[p].nc == F.nc;
+
+    auto open = [&](const cudaIpcMemHandle_t &h) -> void * {
+        void *q = nullptr;
+        if (cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; return nullptr; }
+        c->opened.push_back(q);
+        return q;
+    };
+    if (ok) {
+        c->sp.nranks = nr;
+        c->sp.rank = c->rank;
+        for (int p = 0; p < nr && ok; p++) {
+            if (p == c->rank) { c->sp.mail[p] = c->mail; c->sp.mail_flag[p] = c->flags; continue; }
+            c->sp.mail[p] = (double *)open(all[p].mail);
+            c->sp.mail_flag[p] = (unsigned *)open(all[p].flags);
+            const bool up = p == c->rank - 1, down = p == c->rank + 1;
+            if (!up && !down) continue;
+            for (int k = 0; k < F.nc && ok; k++) {
+                float *b0 = (float *)open(all[p].x[k]), *b1 = (float *)open(all[p].xp[k]);
+                if (up) { c->up_buf[k][0] = b0; c->up_buf[k][1] = b1; }
+                else { c->down_buf[k][0] = b0; c->down_buf[k][1] = b1; }
+            }
+            if (up) { c->up_flags = c->sp.mail_flag[p]; c->up_t1 = all[p].t1; }
+            else { c->down_flags = c->sp.mail_flag[p]; c->down_t0 = all[p].t0; }
+        }
+    }
+    // common verdict
+    int *d_ok = reinterpret_cast<int *>(d_all);
+    const int mine_ok = ok ? 1 : 0;
+    CK(cudaMemcpy(d_ok + c->rank, &mine_ok, sizeof(int), cudaMemcpyHostToDevice));
+    NK(api->AllGather(d_ok + c->rank, d_ok, sizeof(int), /*ncclChar*/ 0, c->comm, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    std::vector<int> oks((size_t)nr);
+    CK(cudaMemcpy(oks.data(), d_ok, sizeof(int) * (size_t)nr, cudaMemcpyDeviceToHost));
+    cudaFree(d_all);
+    for (int p = 0; p < nr; p++) ok = ok && oks[p] == 1;
+    c->p2p_state = ok ? 1 : -1;
+    return J2P_OK;
+}
+
+// the two border rows of the current iterate to both neighbours, over peer memory
+static int exchange_halos_p2p(j2p_session *s, j2p_comm *c) {
+    const FrameDev &F = s->F;
+    const size_t W = (size_t)F.W;
+    const int nr = c->nranks;
+    HaloPeers hp;
+    memset(&hp, 0, sizeof hp);
+    hp.has_up = F.t0 > 0 && c->rank > 0;
+    hp.has_down = F.t1 < F.H && c->rank + 1 < nr;
+    if (!hp.has_up && !hp.has_down) return J2P_OK;
+    hp.nc = F.nc;
+    hp.n4 = (unsigned)(2 * W / 4);
+    for (int k = 0; k < F.nc; k++) {
+        const int b = F.pl[k].x == s->x[k] ? 0 : 1;                       // which physical buffer holds the current iterate (same on every rank)
+        hp.up_src[k] = F.pl[k].x + (size_t)F.t0 * W;
+        hp.down_src[k] = F.pl[k].x + (size_t)(F.t1 - 2) * W;
+        if (hp.has_up) hp.up_dst[k] = c->up_buf[k][b] + (size_t)c->up_t1 * W;              // the upper strip's rows below its last owned row
+        if (hp.has_down) hp.down_dst[k] = c->down_buf[k][b] + (size_t)(c->down_t0 - 2) * W; // the lower strip's rows above its first owned row
+    }
+    // flag words of a rank: [2*nr + 0] "my upper neighbour has delivered", [2*nr + 1] "my lower neighbour has delivered"
+    if (hp.has_up) hp.up_flag = c->up_flags + 2 * nr + 1;
+    if (hp.has_down) hp.down_flag = c->down_flags + 2 * nr + 0;
+    hp.from_up = c->flags + 2 * nr + 0;
+    hp.from_down = c->flags + 2 * nr + 1;
+    CK(launch_halo_exchange(hp, ++c->seq_halo, c->flags + 2 * nr + 2, reinterpret_cast<int *>(c->flags + 2 * nr + 3), s->stream));
+    s->launches++;
+    return J2P_OK;
 }
 
 // the two border rows of the current iterate, all planes, both neighbours: one NCCL group
@@ -847,8 +987,12 @@ extern "C" int j2p_session_iterate_strip(j2p_session *s, j2p_comm *c, unsigned n
         if (!s->uploaded[k]) return fail(J2P_ERR_ARG, "plane %d has not been uploaded", k);
     FrameDev &F = s->F;
     int rc;
+    // peer-memory protocol: opt-in (J2P_STRIP_P2P=1), bound to one session per communicator
+    static const bool want_p2p = [] { const char *e = getenv("J2P_STRIP_P2P"); return e && *e == '1'; }();
+    if (want_p2p && c->p2p_state == 0 && (rc = p2p_bind(c, s, api)) != J2P_OK) return rc;
+    const bool p2p = want_p2p && c->p2p_state == 1 && c->bound == s;
     if (s->next_iter == 0) {
-        if ((rc = exchange_halos_nccl(s, c, api)) != J2P_OK) return rc;
+        if ((rc = p2p ? exchange_halos_p2p(s, c) : exchange_halos_nccl(s, c, api)) != J2P_OK) return rc;
         if ((rc = j2p_session_copy_halo_to_prev(s)) != J2P_OK) return rc;
     }
     for (unsigned i = 0; i < n; i++) {
@@ -856,8 +1000,13 @@ extern "C" int j2p_session_iterate_strip(j2p_session *s, j2p_comm *c, unsigned n
         const float factor = (s->t - 1) / tnext;
         s->t = tnext;
         CK(launch_gradient(F, factor, s->stream));
-        NK(api->AllGather(F.sums, c->gathered, 3, kNcclFloat64, c->comm, s->stream));
-        CK(launch_fold_sums(c->gathered, c->nranks, F.nc, F.norms, s->stream));
+        if (p2p) {
+            CK(launch_sums_exchange(c->sp, F.sums, c->mail, c->flags, ++c->seq_sums, F.nc, F.norms,
+                                    reinterpret_cast<int *>(c->flags + 2 * c->nranks + 3), s->stream));
+        } else {
+            NK(api->AllGather(F.sums, c->gathered, 3, kNcclFloat64, c->comm, s->stream));
+            CK(launch_fold_sums(c->gathered, c->nranks, F.nc, F.norms, s->stream));
+        }
         CK(launch_project(F, factor, s->stream));
         s->launches += 2 + (unsigned)F.nc;
         for (int k = 0; k < F.nc; k++) {                                 // compute.c:438
@@ -866,7 +1015,7 @@ extern "C" int j2p_session_iterate_strip(j2p_session *s, j2p_comm *c, unsigned n
             F.pl[k].xp = tmp;
         }
         s->next_iter++;
-        if ((rc = exchange_halos_nccl(s, c, api)) != J2P_OK) return rc;
+        if ((rc = p2p ? exchange_halos_p2p(s, c) : exchange_halos_nccl(s, c, api)) != J2P_OK) return rc;
     }
     return J2P_OK;
 }

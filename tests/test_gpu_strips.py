@@ -1,6 +1,7 @@
 """Row strips of one frame over several B200s (pytest -m gpu on a box with >= 2 GPUs): the product's
 strip sessions + NCCL, against the single-GPU product result (which the parity tests tie to the
-reference).  Skipped on a single-GPU box."""
+reference).  Skipped on a single-GPU box.  With J2P_STRIP_P2P=1 in the environment the 'native'
+cases run the peer-memory protocol instead of NCCL inside the loop (same assertions)."""
 import os
 import tempfile
 
@@ -35,6 +36,9 @@ def _worker(rank, world, init_file, out_dir, native):
             strips.solve_strips(be, dist, rank, world, CASE['iters'])
         np.savez(os.path.join(out_dir, f'rank{rank}.npz'), rows=rows, **{f'p{c}': be.download(c) for c in range(3)})
         if native:
+            assert lib.j2p_comm_status(comm) == 0, lib.j2p_last_error().decode()
+            if os.environ.get('J2P_STRIP_P2P') == '1' and world <= 8:
+                assert lib.j2p_comm_protocol(comm) == 1, 'the peer-memory protocol was requested but the ranks fell back to NCCL'
             lib.j2p_comm_destroy(comm)
         be.close()
         dist.barrier()

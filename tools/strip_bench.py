@@ -67,6 +67,8 @@ for mode in ('native', 'torchdist'):
         dev, wl = t[0].item(), t[1].item()
         print(f'strips[{mode}] N={world} {args.width}x{args.height} {args.subsampling} {args.iterations} it: device {dev*1e3:.1f} ms '
               f'(wall {wl*1e3:.1f} ms)  {pix / dev / 1e6:.0f} Mpix-it/s  ({dev / args.iterations * 1e6:.0f} us/iteration)', flush=True)
+        if mode == 'native':
+            print(f'strips[native] protocol: {"peer memory" if lib.j2p_comm_protocol(comm) else "NCCL"}, status {lib.j2p_comm_status(comm)}', flush=True)
         print(f'strips[{mode}] N={world} checksum {float(np.float64(be.download(0)).sum()):.4f}', flush=True)
 lib.j2p_comm_destroy(comm)
 be.close()
