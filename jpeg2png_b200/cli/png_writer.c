@@ -49,6 +49,71 @@ static int put_chunk(FILE *f, const char *type, const uint8_t *data, size_t len)
         return fwrite(hdr, 1, 8, f) == 8 && (len == 0 || fwrite(data, 1, len, f) == len) && fwrite(tail, 1, 4, f) == 4 ? 0 : -1;
 }
 
+/* One zlib stream made of independently deflated pieces (the pigz construction): every piece but
+ * the last ends with Z_SYNC_FLUSH — an empty stored block that pads to a byte boundary and leaves
+ * the stream open — the last with Z_FINISH; the 2-byte zlib header goes in front and the Adler-32
+ * of the whole input (combined from the per-piece checksums) behind.  Pieces cost ~1 % of
+ * compression ratio (no history across them) and make an 8K frame's 100 MB of RGB a job for all
+ * host threads instead of several seconds on one.  Inside the file-parallel loop of the command
+ * line OpenMP runs the inner loop serially (nested parallelism is off), which is what we want. */
+#define J2P_PIECE ((size_t)1 << 20)
+#define J2P_FAIL() do { _Pragma("omp atomic write") failed = 1; } while (0)
+
+static uint8_t *deflate_pieces(const uint8_t *raw, size_t len, size_t *zlen) {
+        const size_t np = (len + J2P_PIECE - 1) / J2P_PIECE;
+        uint8_t **buf = calloc(np, sizeof *buf);
+        size_t *blen = calloc(np, sizeof *blen);
+        uLong *adl = calloc(np, sizeof *adl);
+        if (!buf || !blen || !adl) { free(buf); free(blen); free(adl); return NULL; }
+        int failed = 0;
+#pragma omp parallel for schedule(dynamic)
+        for (long i = 0; i < (long)np; i++) {
+                const size_t off = (size_t)i * J2P_PIECE, n = len - off < J2P_PIECE ? len - off : J2P_PIECE;
+                z_stream zs;
+                memset(&zs, 0, sizeof zs);
+                if (deflateInit2(&zs, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { J2P_FAIL(); continue; }
+                const size_t cap = deflateBound(&zs, (uLong)n) + 64;
+                buf[i] = malloc(cap);
+                if (buf[i]) {
+                        zs.next_in = (Bytef *)(raw + off);
+                        zs.avail_in = (uInt)n;
+                        zs.next_out = buf[i];
+                        zs.avail_out = (uInt)cap;
+                        const int last = (size_t)i + 1 == np;
+                        const int rc = deflate(&zs, last ? Z_FINISH : Z_SYNC_FLUSH);
+                        if ((last ? rc != Z_STREAM_END : rc != Z_OK) || zs.avail_in != 0 || zs.avail_out == 0) J2P_FAIL();
+                        blen[i] = cap - zs.avail_out;
+                        adl[i] = adler32(adler32(0L, Z_NULL, 0), raw + off, (uInt)n);
+                } else {
+                        J2P_FAIL();
+                }
+                deflateEnd(&zs);
+        }
+        uint8_t *z = NULL;
+        if (!failed) {
+                size_t total = 2 + 4;
+                for (size_t i = 0; i < np; i++) total += blen[i];
+                z = malloc(total);
+                if (z) {
+                        size_t pos = 0;
+                        z[pos++] = 0x78;                                 /* deflate, 32 KB window */
+                        z[pos++] = 0x9C;                                 /* default compression, check bits */
+                        uLong a = adler32(0L, Z_NULL, 0);
+                        for (size_t i = 0; i < np; i++) {
+                                memcpy(z + pos, buf[i], blen[i]);
+                                pos += blen[i];
+                                const size_t off = i * J2P_PIECE, n = len - off < J2P_PIECE ? len - off : J2P_PIECE;
+                                a = adler32_combine(a, adl[i], (z_off_t)n);
+                        }
+                        z[pos++] = (uint8_t)(a >> 24); z[pos++] = (uint8_t)(a >> 16); z[pos++] = (uint8_t)(a >> 8); z[pos++] = (uint8_t)a;
+                        *zlen = pos;
+                }
+        }
+        for (size_t i = 0; i < np; i++) free(buf[i]);
+        free(buf); free(blen); free(adl);
+        return z;
+}
+
 int j2p_write_png(FILE *out, unsigned w, unsigned h, unsigned bits, const float *y, unsigned ys, const float *cb, unsigned cbs,
                   const float *cr, unsigned crs) {
         if (bits != 8 && bits != 16) return -1;
@@ -57,10 +122,18 @@ int j2p_write_png(FILE *out, unsigned w, unsigned h, unsigned bits, const float 
         if (!raw) return -1;
         for (unsigned i = 0; i < h; i++) raw[(size_t)i * stride] = 0;          /* filter 0 (None) */
         j2p_ycc_to_rgb(w, h, bits, y, ys, cb, cbs, cr, crs, raw + 1, stride);
-        uLongf zlen = compressBound((uLong)(stride * h));
-        uint8_t *z = malloc(zlen);
+        size_t zlen = 0;
+        uint8_t *z = NULL;
+        if (stride * h > 2 * J2P_PIECE) {
+                z = deflate_pieces(raw, stride * h, &zlen);
+        } else {
+                uLongf zl = compressBound((uLong)(stride * h));
+                z = malloc(zl);
+                if (z && compress2(z, &zl, raw, (uLong)(stride * h), 6) == Z_OK) zlen = zl;
+                else { free(z); z = NULL; }
+        }
         int rc = -1;
-        if (z && compress2(z, &zlen, raw, (uLong)(stride * h), 6) == Z_OK) {
+        if (z) {
                 static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
                 const uint8_t ihdr[13] = {(uint8_t)(w >> 24), (uint8_t)(w >> 16), (uint8_t)(w >> 8), (uint8_t)w, (uint8_t)(h >> 24), (uint8_t)(h >> 16),
                                           (uint8_t)(h >> 8), (uint8_t)h, (uint8_t)bits, 2 /* truecolour */, 0, 0, 0};

@@ -170,6 +170,44 @@ def test_png_writer_roundtrip(codecs, tmp_path):
             assert (np.asarray(Image.open(path)).reshape(-1) == want).all()
 
 
+def test_png_writer_large_image_pieced_deflate(codecs, tmp_path):
+    """> 2 MB of scanlines: the IDAT stream is assembled from independently deflated 1 MB pieces
+    (png_writer.c); it must still be ONE valid zlib stream with the right Adler-32 and pixels."""
+    codecs.j2p_write_png.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint]
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fclose.argtypes = [C.c_void_p]
+    rng = np.random.default_rng(21)
+    w, h = 1203, 911                                    # 3.3 MB at 8 bit, 6.6 MB at 16 bit; odd sizes on purpose
+    yy, xx = np.mgrid[0:h, 0:w]
+    y = (128 + 90 * np.sin(xx / 37.0) * np.cos(yy / 23.0) + rng.normal(0, 3, (h, w))).astype(np.float32)
+    cb = (40 * np.sign(np.sin(xx / 50.0))).astype(np.float32)
+    cr = rng.normal(0, 50, (h, w)).astype(np.float32)
+    for bits in (8, 16):
+        path = str(tmp_path / f'big{bits}.png')
+        f = libc.fopen(path.encode(), b'wb')
+        assert codecs.j2p_write_png(f, w, h, bits, y.ctypes.data, w, cb.ctypes.data, w, cr.ctypes.data, w) == 0
+        libc.fclose(f)
+        want = np.zeros(w * h * 3 * (bits // 8), np.uint8)
+        H.load_oracle().oracle_ycc_to_rgb(w, h, bits, y.ctypes.data, w, cb.ctypes.data, w, cr.ctypes.data, w, want.ctypes.data)
+        raw = open(path, 'rb').read()
+        pos, idat = 8, b''
+        while pos < len(raw):
+            ln = int.from_bytes(raw[pos:pos + 4], 'big')
+            typ, body = raw[pos + 4:pos + 8], raw[pos + 8:pos + 8 + ln]
+            assert zlib.crc32(typ + body) == int.from_bytes(raw[pos + 8 + ln:pos + 12 + ln], 'big')
+            if typ == b'IDAT':
+                idat += body
+            pos += 12 + ln
+        d = zlib.decompressobj()
+        rows = d.decompress(idat)
+        assert d.eof and d.unused_data == b'', 'not exactly one complete zlib stream'
+        rows = np.frombuffer(rows, np.uint8).reshape(h, 1 + w * 3 * (bits // 8))
+        assert (rows[:, 0] == 0).all() and (rows[:, 1:].reshape(-1) == want).all()
+        if bits == 8:
+            assert (np.asarray(Image.open(path)).reshape(-1) == want).all()
+
+
 @pytest.mark.parametrize('w,h,sampling,ri', [
     (64, 48, [(1, 1), (1, 1), (1, 1)], 0),
     (70, 50, [(2, 2), (1, 1), (1, 1)], 0),          # 4:2:0, MCU padding dropped on the right and bottom
