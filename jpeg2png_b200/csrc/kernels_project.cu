@@ -11,6 +11,8 @@
 namespace j2p {
 
 cudaError_t launch_project_tile(const FrameDev &F, int c, int count, float factor, cudaStream_t s);
+cudaError_t configure_project_tile22();
+cudaError_t launch_project_tile22(const FrameDev &F, int c, int count, float factor, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------
 // k_project — 8 threads per coefficient block (thread j owns row j), 32 blocks per CTA.
@@ -310,7 +312,15 @@ __global__ void k_init_plane(const float *fdata, float *x, float *xp, int W, int
 // ------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------
-cudaError_t configure_project_kernels() { return cudaSuccess; }   // nothing to opt into: static shared memory only
+// J2P_PROJ_TILE22=1: 2x2 planes through kernels_project_tile22.cu instead of k_project<2,2>
+// (opt-in until it has been validated on the GPU, see that file)
+static bool g_tile22 = false;
+
+cudaError_t configure_project_kernels() {
+    const char *e = getenv("J2P_PROJ_TILE22");
+    g_tile22 = e && *e == '1';
+    return g_tile22 ? configure_project_tile22() : cudaSuccess;
+}
 
 // strip sessions: fold the per-rank sums of g^2 in rank order (deterministic), then the norms of
 // compute.c:200-206 and their reciprocals
@@ -356,6 +366,15 @@ cudaError_t launch_project(const FrameDev &Fin, float factor, cudaStream_t s) {
                    F.pl[c + count].ch == P.ch)
                 count++;
             const cudaError_t eb = launch_project_tile(F, c, count, factor, s);
+            if (eb != cudaSuccess) return eb;
+            c += count - 1;
+        }
+        else if (P.sw == 2 && P.sh == 2 && g_tile22 && !F.log_on) {
+            int count = 1;      // Cb and Cr share one launch
+            while (c + count < F.nc && F.pl[c + count].sw == 2 && F.pl[c + count].sh == 2 && F.pl[c + count].cw == P.cw &&
+                   F.pl[c + count].ch == P.ch)
+                count++;
+            const cudaError_t eb = launch_project_tile22(F, c, count, factor, s);
             if (eb != cudaSuccess) return eb;
             c += count - 1;
         }
