@@ -130,3 +130,31 @@ def test_rgb_conversion_restatement():
     ora.oracle_ycc_to_rgb(6, 1, 16, y.ctypes.data, 6, cb.ctypes.data, 6, cr.ctypes.data, 6, out16.ctypes.data)
     v = out16.reshape(6, 3, 2)
     assert (int(v[1, 0, 0]) << 8 | int(v[1, 0, 1])) == 255 * 256
+
+
+@needs_ref
+@pytest.mark.parametrize('seed', range(16))
+def test_oracle_matches_reference_random_sweep(seed):
+    """Randomised configurations (plane sizes, sampling factors up to 3x4, zero and non-zero weights,
+    single-plane and joint mode, planes smaller than the frame): restatement == compiled reference."""
+    rng = np.random.default_rng(1000 + seed)
+    nplanes = 3
+    samp = [(1, 1)] + [(int(rng.integers(1, 4)), int(rng.integers(1, 5))) for _ in range(2)]
+    fw, fh = 8 * int(rng.integers(2, 9)), 8 * int(rng.integers(2, 7))
+    dims = []
+    for (sw, sh) in samp:
+        cw, ch = -(-fw // sw), -(-fh // sh)
+        cw, ch = -(-cw // 8) * 8, -(-ch // 8) * 8
+        if rng.random() < 0.3 and cw > 8:
+            cw -= 8                                               # a plane that does not cover the frame
+        dims.append((cw, ch))
+    img = synth.random_coefs(dims, samp, seed=seed, amplitude=int(rng.integers(5, 60)), qmax=int(rng.integers(2, 80)))
+    joint = rng.random() < 0.6
+    channels = [0, 1, 2] if joint else [int(rng.integers(0, nplanes))]
+    weight = float(rng.choice([0.0, 0.1, 0.3, 1.0]))
+    pw = [float(rng.choice([0.0, 0.001, 0.05])) for _ in channels]
+    iters = int(rng.integers(1, 25))
+    f = H.decode_planes(img, channels)
+    a = H.run_compute('ref', img, channels, weight, pw, iters, [p.copy() for p in f])
+    b = H.run_compute('oracle', img, channels, weight, pw, iters, [p.copy() for p in f])
+    H.assert_bit_identical(b, a, f'sweep seed {seed}: samp {samp} dims {dims} channels {channels} w {weight} p {pw} i {iters}')
