@@ -10,9 +10,9 @@
 
 namespace j2p {
 
-cudaError_t launch_project_tile(const FrameDev &F, int c, int count, float factor, cudaStream_t s);
+cudaError_t launch_project_tile(const FrameDev &F, int c, int count, float factor, cudaStream_t s, int *nlaunch);
 cudaError_t configure_project_tile22();
-cudaError_t launch_project_tile22(const FrameDev &F, int c, int count, float factor, cudaStream_t s);
+cudaError_t launch_project_tile22(const FrameDev &F, int c, int count, float factor, cudaStream_t s, int *nlaunch);
 
 // ------------------------------------------------------------------------------------------
 // k_project — 8 threads per coefficient block (thread j owns row j), 32 blocks per CTA.
@@ -339,7 +339,9 @@ cudaError_t launch_fold_sums(const double *sums_by_rank, int nranks, int nc, flo
     return cudaGetLastError();
 }
 
-cudaError_t launch_project(const FrameDev &Fin, float factor, cudaStream_t s) {
+// *nlaunch: number of kernels launched (planes of one geometry share a launch)
+cudaError_t launch_project(const FrameDev &Fin, float factor, cudaStream_t s, int *nlaunch) {
+    *nlaunch = 0;
     // the projection is block-local: it only sees the rows the session owns (no halo rows)
     FrameDev F = Fin;
     if (F.t0 != 0 || F.t1 != F.H) {
@@ -358,6 +360,7 @@ cudaError_t launch_project(const FrameDev &Fin, float factor, cudaStream_t s) {
         G.c = c;
         G.gx = (F.W + tw - 1) / tw;
         const dim3 grid(G.gx, (F.H + th - 1) / th);
+        const int before = *nlaunch;
         if (F.log_on && P.sw == 1 && P.sh == 1) {
             k_project<1, 1><<<grid, P_NT, 0, s>>>(F, G, factor);                // the variant that also sums the log terms
         } else if (P.sw == 1 && P.sh == 1) {
@@ -365,7 +368,7 @@ cudaError_t launch_project(const FrameDev &Fin, float factor, cudaStream_t s) {
             while (c + count < F.nc && F.pl[c + count].sw == 1 && F.pl[c + count].sh == 1 && F.pl[c + count].cw == P.cw &&
                    F.pl[c + count].ch == P.ch)
                 count++;
-            const cudaError_t eb = launch_project_tile(F, c, count, factor, s);
+            const cudaError_t eb = launch_project_tile(F, c, count, factor, s, nlaunch);
             if (eb != cudaSuccess) return eb;
             c += count - 1;
         }
@@ -374,7 +377,7 @@ cudaError_t launch_project(const FrameDev &Fin, float factor, cudaStream_t s) {
             while (c + count < F.nc && F.pl[c + count].sw == 2 && F.pl[c + count].sh == 2 && F.pl[c + count].cw == P.cw &&
                    F.pl[c + count].ch == P.ch)
                 count++;
-            const cudaError_t eb = launch_project_tile22(F, c, count, factor, s);
+            const cudaError_t eb = launch_project_tile22(F, c, count, factor, s, nlaunch);
             if (eb != cudaSuccess) return eb;
             c += count - 1;
         }
@@ -382,6 +385,7 @@ cudaError_t launch_project(const FrameDev &Fin, float factor, cudaStream_t s) {
         else if (P.sw == 2 && P.sh == 1) k_project<2, 1><<<grid, P_NT, 0, s>>>(F, G, factor);
         else if (P.sw == 1 && P.sh == 2) k_project<1, 2><<<grid, P_NT, 0, s>>>(F, G, factor);
         else k_project<0, 0><<<grid, P_NT, 0, s>>>(F, G, factor);
+        if (*nlaunch == before) *nlaunch += 1;                       // one of the direct k_project<> launches above
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }

@@ -253,12 +253,13 @@ cudaError_t configure_project_tile22() {
 
 // F: already restricted to the rows the session owns (launch_project).  Projects planes
 // c .. c+count-1, which must all be 2x2 planes with the same coefficient grid.
-cudaError_t launch_project_tile22(const FrameDev &F, int c, int count, float factor, cudaStream_t s) {
+cudaError_t launch_project_tile22(const FrameDev &F, int c, int count, float factor, cudaStream_t s, int *nlaunch) {
     const PlaneDev &P = F.pl[c];
     const int bw = P.cw >> 3, bh = P.ch >> 3;
     const dim3 grid((bw + P22_NB - 1) / P22_NB, bh, count);
     k_project_tile22<<<grid, P22_NT, P22_SMEM, s>>>(F, c, factor);
     cudaError_t e = cudaGetLastError();
+    *nlaunch += 1;
     for (int k = c; k < c + count && e == cudaSuccess; k++) {
         const PlaneDev &Q = F.pl[k];
         if (2 * Q.cw < F.W || 2 * Q.ch < F.H) {
@@ -267,6 +268,7 @@ cudaError_t launch_project_tile22(const FrameDev &F, int c, int count, float fac
             if (blocks > 148 * 8) blocks = 148 * 8;
             k_step_uncovered22<<<blocks, 256, 0, s>>>(F, k, factor);
             e = cudaGetLastError();
+            *nlaunch += 1;
         }
     }
     return e;

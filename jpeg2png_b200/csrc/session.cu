@@ -35,7 +35,7 @@ namespace j2p {
 int grad_cta_count(int W, int H);
 cudaError_t configure_kernels();
 cudaError_t launch_gradient(const FrameDev &F, float factor, cudaStream_t s);
-cudaError_t launch_project(const FrameDev &F, float factor, cudaStream_t s);
+cudaError_t launch_project(const FrameDev &F, float factor, cudaStream_t s, int *nlaunch);
 cudaError_t launch_fold_sums(const double *sums_by_rank, int nranks, int nc, float *norms, cudaStream_t s);
 cudaError_t launch_decode(const int16_t *data, const float *q_host, float *out, int cw, int ch, cudaStream_t s);
 cudaError_t launch_init_plane(const float *fdata, float *x, float *xp, int W, int H, int cw, int ch, int sw, int sh,
@@ -498,14 +498,15 @@ static int one_iteration(j2p_session *s, cudaEvent_t e0, cudaEvent_t e1, cudaEve
         F.log_slot = (int)((s->next_log_iter + 1) & 1);
         CK(cudaMemsetAsync(F.logsums + 2 + 3 * F.log_slot, 0, 3 * sizeof(double), s->stream));
     }
-    CK(launch_project(F, factor, s->stream));
+    int nproj = 0;
+    CK(launch_project(F, factor, s->stream, &nproj));
     if (F.log_on) {
         CK(cudaMemcpyAsync(s->log_host, F.logsums, 8 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
         s->log_host_iter = s->next_log_iter;
         s->next_log_iter++;
     }
     if (e2) CK(cudaEventRecord(e2, s->stream));
-    s->launches += 1 + (unsigned)F.nc;
+    s->launches += 1 + (unsigned)nproj;
     for (int c = 0; c < F.nc; c++) {                                    // compute.c:438
         float *tmp = F.pl[c].x;
         F.pl[c].x = F.pl[c].xp;
@@ -547,8 +548,9 @@ extern "C" int j2p_session_project(j2p_session *s, const double *sums_by_rank, u
     CK(cudaSetDevice(s->device));
     FrameDev &F = s->F;
     CK(launch_fold_sums(sums_by_rank, (int)nranks, F.nc, F.norms, s->stream));
-    CK(launch_project(F, s->pending_factor, s->stream));
-    s->launches += 1 + (unsigned)F.nc;
+    int nproj = 0;
+    CK(launch_project(F, s->pending_factor, s->stream, &nproj));
+    s->launches += 1 + (unsigned)nproj;                                 // the fold kernel + the projection launches
     for (int c = 0; c < F.nc; c++) {                                    // compute.c:438
         float *tmp = F.pl[c].x;
         F.pl[c].x = F.pl[c].xp;
@@ -1007,8 +1009,9 @@ extern "C" int j2p_session_iterate_strip(j2p_session *s, j2p_comm *c, unsigned n
             NK(api->AllGather(F.sums, c->gathered, 3, kNcclFloat64, c->comm, s->stream));
             CK(launch_fold_sums(c->gathered, c->nranks, F.nc, F.norms, s->stream));
         }
-        CK(launch_project(F, factor, s->stream));
-        s->launches += 2 + (unsigned)F.nc;
+        int nproj = 0;
+        CK(launch_project(F, factor, s->stream, &nproj));
+        s->launches += 2 + (unsigned)nproj;                              // gradient, sums exchange / fold, projection launches
         for (int k = 0; k < F.nc; k++) {                                 // compute.c:438
             float *tmp = F.pl[k].x;
             F.pl[k].x = F.pl[k].xp;
