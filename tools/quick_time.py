@@ -9,8 +9,18 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from jpeg2png_b200 import abi, synth  # noqa: E402
 
-libs = sys.argv[1:] or [abi.PRODUCT_LIB]
-img = synth.synth_coefs(3840, 2160, 50, '4:4:4', 1237)
+# optional leading frame spec: --frame W H Q SUBSAMPLING   (default: the bench workload)
+argv = sys.argv[1:]
+frame = (3840, 2160, 50, '4:4:4')
+if argv[:1] == ['--frame']:
+    frame = (int(argv[1]), int(argv[2]), int(argv[3]), argv[4])
+    argv = argv[5:]
+libs = argv or [abi.PRODUCT_LIB]
+if frame[0] * frame[1] > 3840 * 2160:          # large frames: tile a quarter-size cartoon (seconds instead of half a minute)
+    base = synth.synth_coefs(-(-frame[0] // 64) * 16, -(-frame[1] // 64) * 16, frame[2], frame[3], 1237)
+    img = synth.tile_coefs(base, 4, 4, frame[0], frame[1])
+else:
+    img = synth.synth_coefs(frame[0], frame[1], frame[2], frame[3], 1237)
 for path in libs:
     lib = abi.declare_product(C.CDLL(path, mode=C.RTLD_LOCAL))
     d = abi.FrameDesc()
@@ -29,7 +39,7 @@ for path in libs:
     mg, mp = C.c_float(), C.c_float()
     lib.j2p_session_profile(s, 10, C.byref(mg), C.byref(mp))
     lib.j2p_session_profile(s, 40, C.byref(mg), C.byref(mp))
-    out = np.empty((2160, 3840), np.float32)
+    out = np.empty((img.frame_h, img.frame_w), np.float32)
     lib.j2p_session_download(s, 0, out.ctypes.data)
     print(f'{os.path.basename(path):40s} gradient {mg.value*1e3:8.1f} us  project {mp.value*1e3:8.1f} us  sum {(mg.value+mp.value)*1e3:8.1f} us  checksum {float(np.float64(out).sum()):.6f}')
     lib.j2p_session_destroy(s)
