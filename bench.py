@@ -159,13 +159,29 @@ def cpu_solve_rate(img, fdata, iterations, kind):
     return img.width * img.height * iterations / dt / 1e6, dt
 
 
+def usable_cpus():
+    """CPUs this process may really use: the affinity mask capped by the cgroup CPU quota (the GPU
+    boxes show 128 hardware threads but grant 16 CPUs; an OpenMP team wider than the quota spins
+    itself into being throttled, which would make the CPU arm look slower than it is)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    try:
+        quota, period = open('/sys/fs/cgroup/cpu.max').read().split()[:2]
+        if quota != 'max':
+            n = min(n, max(1, -(-int(quota) // int(period))))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
 def cpu_kind_and_cores():
     from tests import helpers as H
     if H.have_ref():
         lib = H.load_ref()
-        return 'ref', 'reference', int(lib.ref_glue_max_threads())
+        cores = min(int(lib.ref_glue_max_threads()), usable_cpus())
+        lib.ref_glue_set_threads(cores)
+        return 'ref', 'reference', cores
     H.build_oracle_libs()
-    return 'oracle', 'port', os.cpu_count() or 1
+    return 'oracle', 'port', usable_cpus()
 
 
 def cpu_warmup(kind):
