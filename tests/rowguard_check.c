@@ -53,6 +53,30 @@ int main(int argc, char **argv) {
                         }
                 }
         }
+        /* ---- the two power-of-two rewrites of the TGV stage (kernels_gradient.cu) -------------------
+         *   2*RN((u/2)^2)                      == RN(u * (u/2))
+         *   a2 * (-(2gxx + 2s + 2gyy) / n)     == (-2 a2) * (((s + gxx) + gyy) / n)
+         * on values in the range the fast path admits (differences >= 2^-58 in magnitude or 0, norms in [2^-40, 2^40]). */
+        long rewrites = 0;
+        for (long it = 0; it < n; it++) {
+                const int e = (int)(next() % 70) - 50;                  /* magnitudes 2^-50 .. 2^19 */
+                const float gxx = ldexpf((float)((int)(next() % 4001) - 2000) + (float)(next() & 0xffff) / 65536.f, e);
+                const float gyy = ldexpf((float)((int)(next() % 4001) - 2000) + (float)(next() & 0xffff) / 65536.f, e - (int)(next() % 3));
+                const float u = ldexpf((float)((int)(next() % 4001) - 2000) + (float)(next() & 0xffff) / 65536.f, e + (int)(next() % 3) - 1);
+                const float sgm = u * 0.5f;
+                const float a2 = 0.05f + (float)(next() % 1000) / 500.f;
+                const float nn = sqrtf(gxx * gxx + 2.f * (sgm * sgm) + gyy * gyy);
+                if (!(nn >= 9.094947017729282e-13f && nn <= 1.099511627776e12f)) continue;
+                const float lhs1 = 2.f * (sgm * sgm), rhs1 = u * sgm;
+                const float lhs2 = a2 * (-((2.f * gxx + 2.f * sgm) + 2.f * gyy) / nn);
+                const float rhs2 = (-2.f * a2) * (((sgm + gxx) + gyy) / nn);
+                rewrites++;
+                if (!(lhs1 == rhs1) || !(lhs2 == rhs2)) {
+                        if (bad < 10) printf("REWRITE MISMATCH gxx=%a s=%a gyy=%a n=%a: %a vs %a, %a vs %a\n", gxx, sgm, gyy, nn, lhs1, rhs1, lhs2, rhs2);
+                        bad++;
+                }
+        }
+        printf("rowguard_check: %ld rewrite pairs compared\n", rewrites);
         printf("rowguard_check: %ld non-zero numerators, %ld below 2^-60; smallest seen 2^%.2f\n", nonzero, bad, log2f(smallest));
         return bad ? 1 : 0;
 }
