@@ -81,7 +81,11 @@ static void fill(struct dec *d) {
         }
 }
 static inline int getbits(struct dec *d, int n) {
-        if (n == 0) return 0;
+        if (n <= 0) return 0;
+        if (n > 16) {                                    /* only a corrupt Huffman table can ask for more (F.1.2.1.1: at most 15/16) */
+                fail(d, "corrupt jpeg: bad magnitude category");
+                return 0;
+        }
         if (d->nbits < n) fill(d);
         const int v = (int)(d->acc >> (32 - n));
         d->acc <<= n;
@@ -115,7 +119,7 @@ static int decode_huff(struct dec *d, const struct huff *h) {
         fail(d, "corrupt jpeg: bad huffman code");
         return 0;
 }
-static inline int extend(int v, int s) { return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v; }   /* F.2.2.1 */
+static inline int extend(int v, int s) { return (s < 1 || s > 16) ? 0 : (v < (1 << (s - 1)) ? v - (1 << s) + 1 : v); }   /* F.2.2.1 */
 
 /* ---- block decoders ------------------------------------------------------------------------ */
 static void block_sequential(struct dec *d, struct comp *c, int16_t *b) {
