@@ -22,6 +22,12 @@ BASELINE config 5 style): every rank solves its own frame on its own GPU, no dat
 collective; NCCL is only used for the barrier and the max-over-ranks of the device time.
 Scaling is therefore "weak".
 
+  strong    (beside the weak-scaling `value`) ONE 7680x4320 4:2:0 frame cut into N row strips, the
+            only multi-GPU mode that communicates: device time per iteration, speed-up over the
+            whole frame on one GPU measured in the same run, bit-identity with that 1-GPU result.
+  parity_at_size  N=1: the product's first 20 iterations of the bench frame against the
+            reference's, bit for bit (the cpu_baseline call produces the reference planes anyway).
+
 `--impl reference` times the reference CPU implementation instead (rank 0 only).
 """
 from __future__ import annotations
@@ -149,12 +155,14 @@ def make_frame(seed):
 # ---------------------------------------------------------------------------------------------
 # reference arm / cpu baseline
 # ---------------------------------------------------------------------------------------------
-def cpu_solve_rate(img, fdata, iterations, kind):
+def cpu_solve_rate(img, fdata, iterations, kind, keep=None):
     """Time ONE compute() call of `iterations` iterations with the CPU checker (host marshalling
-    excluded); returns (Mpix-it/s, seconds)."""
+    excluded); returns (Mpix-it/s, seconds).  keep: a list that receives the result planes."""
     from tests import helpers as H
     timer = {}
-    H.run_compute(kind, img, [0, 1, 2], WEIGHT, [PWEIGHT] * 3, iterations, fdata, timer=timer)
+    out = H.run_compute(kind, img, [0, 1, 2], WEIGHT, [PWEIGHT] * 3, iterations, fdata, timer=timer)
+    if keep is not None:
+        keep.extend(out)
     dt = timer['seconds']
     return img.width * img.height * iterations / dt / 1e6, dt
 
@@ -174,14 +182,46 @@ def usable_cpus():
 
 
 def cpu_kind_and_cores():
+    """Which CPU checker is the baseline, and with how many threads.  The OpenMP team is set
+    explicitly to the CPUs this process may use: torchrun exports OMP_NUM_THREADS=1 to its workers,
+    which would otherwise silently shrink the reference arm at N > 1."""
     from tests import helpers as H
     if H.have_ref():
         lib = H.load_ref()
-        cores = min(int(lib.ref_glue_max_threads()), usable_cpus())
+        cores = usable_cpus()
         lib.ref_glue_set_threads(cores)
         return 'ref', 'reference', cores
     H.build_oracle_libs()
-    return 'oracle', 'port', usable_cpus()
+    return 'oracle', 'port', 1
+
+
+def cpu_separate_mode_rate(img, fdata, iterations, kind):
+    """The reference's -s mode (jpeg2png.c:147-152): three concurrent compute(1, ...) calls, one
+    per plane, weights {w, 0, 0}.  Three host threads here (ctypes releases the GIL)."""
+    from tests import helpers as H
+    weights = [WEIGHT, 0.0, 0.0]
+    t0 = time.perf_counter()
+    ts = [threading.Thread(target=H.run_compute, args=(kind, img, [c], weights[c], [PWEIGHT], iterations, [fdata[c]])) for c in range(3)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    dt = time.perf_counter() - t0
+    return img.width * img.height * iterations / dt / 1e6, dt
+
+
+def cpu_file_parallel_rate(img, fdata, iterations, kind, nfiles):
+    """The reference's file loop (jpeg2png.c:330): `nfiles` frames solved concurrently, each in
+    joint mode.  Aggregate Mpix-it/s over all of them."""
+    from tests import helpers as H
+    t0 = time.perf_counter()
+    ts = [threading.Thread(target=H.run_compute, args=(kind, img, [0, 1, 2], WEIGHT, [PWEIGHT] * 3, iterations, fdata)) for _ in range(nfiles)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    dt = time.perf_counter() - t0
+    return nfiles * img.width * img.height * iterations / dt / 1e6, dt
 
 
 def cpu_warmup(kind):
@@ -200,7 +240,7 @@ def run_reference_arm(args, rank, world):
     cpu_warmup(kind)
     # bounded sample: per-iteration cost does not depend on the iteration count, so every step
     # solves the same frame for `it` iterations, sized so the whole run stays within ~3 minutes
-    budget_s = 150.0
+    budget_s = 120.0
     per_iter_s = 0.65
     it = int(max(1, min(ITERATIONS, budget_s / ((args.steps + args.warmup) * per_iter_s))))
     from tests import helpers as H
@@ -349,6 +389,10 @@ def run_product_arm(args, rank, local_rank, world):
         stop.set()
         sampler.join(timeout=3)
 
+    strong = None
+    if os.environ.get('J2P_BENCH_STRONG', '1') != '0':
+        strong = run_strong(lib, torch, dist, rank, local_rank, world)
+
     if rank == 0:
         pix_it = WIDTH * HEIGHT * ITERATIONS
         value = world * pix_it * args.steps / (ms_total * 1e-3) / 1e6
@@ -372,14 +416,33 @@ def run_product_arm(args, rank, local_rank, world):
                                   'gbs': (gb + pb) / ((mg.value + mp.value) * 1e-3) / 1e9,
                                   'frac': (gb + pb) / ((mg.value + mp.value) * 1e-3) / 1e9 / peak}}
         cpu = None
+        parity_at_size = None
         if world == 1:
             kind, label, cores = cpu_kind_and_cores()
             cpu_warmup(kind)
             sample_it = 20
-            rate, secs = cpu_solve_rate(img, fdata, sample_it, kind)
+            ref_planes = []
+            rate, secs = cpu_solve_rate(img, fdata, sample_it, kind, keep=ref_planes)
+            # parity AT THE BENCHMARKED SIZE: the product's first `sample_it` iterations of the same
+            # frame through compute(), bit for bit against what the reference just produced
+            from tests import helpers as H
+            got = H.run_compute('product', img, [0, 1, 2], WEIGHT, [PWEIGHT] * 3, sample_it, fdata)
+            same = all((H.bits(a) == H.bits(b)).all() for a, b in zip(got, ref_planes))
+            parity_at_size = {'result': 'bit-identical' if same else 'MISMATCH', 'against': label,
+                              'what': f'{WIDTH}x{HEIGHT} 4:4:4 joint, first {sample_it} iterations, all three planes'}
+            if not same:
+                parity_at_size['max_abs_diff'] = float(max(np.max(np.abs(a.astype(np.float64) - b)) for a, b in zip(got, ref_planes)))
+            del got, ref_planes
+            sep_rate, sep_secs = cpu_separate_mode_rate(img, fdata, 10, kind)
+            nfiles = max(1, min(4, cores // 3))
+            fp_rate, fp_secs = cpu_file_parallel_rate(img, fdata, 5, kind, nfiles)
             cpu = {'value': rate, 'unit': 'Mpix-it/s', 'cores': cores, 'kind': label,
                    'sample': f'{WIDTH}x{HEIGHT} 4:4:4 joint, {sample_it} of {ITERATIONS} iterations, one call, {secs:.1f} s '
-                             '(joint mode threads over the 3 planes only; TV/TGV passes are serial, compute.c:233,253,260)'}
+                             '(joint mode threads over the 3 planes only; TV/TGV passes are serial, compute.c:233,253,260)',
+                   'separate_mode': {'value': sep_rate, 'unit': 'Mpix-it/s',
+                                     'sample': f'-s mode, 3 concurrent compute(1,..) (jpeg2png.c:147-152), 10 iterations, {sep_secs:.1f} s'},
+                   'file_parallel': {'value': fp_rate, 'unit': 'Mpix-it/s',
+                                     'sample': f'{nfiles} frames solved concurrently, joint mode (jpeg2png.c:330), 5 iterations each, {fp_secs:.1f} s'}}
         line = {
             'metric': METRIC, 'value': value, 'unit': 'Mpix-it/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -394,11 +457,123 @@ def run_product_arm(args, rank, local_rank, world):
             'gpu_launches': launches,
             'roofline': roofline,
             'cpu_baseline': cpu,
+            'parity_at_size': parity_at_size,
+            'strong': strong,
             'checksum': {'resident': checksum, 'e2e': e2e_checksum},
         }
+        line['roofline']['iteration_frac'] = roofline['iteration']['frac']
         emit(line, world)
     if dist is not None:
         dist.destroy_process_group()
+
+
+STRONG = dict(width=7680, height=4320, quality=10, subsampling='4:2:0', iterations=100, seed=1238)
+
+
+def run_strong(lib, torch, dist, rank, local_rank, world):
+    """Strong scaling of ONE frame (BASELINE config 4's frame: 7680x4320 Q10 4:2:0, joint, 100
+    iterations here): the frame is cut into `world` MCU-aligned row strips, one per GPU
+    (j2p_session_create_strip); an iteration is the two solver kernels with the exchanges inside
+    them over NVLink peer memory (j2p_session_iterate_strip).  Device time with CUDA
+    events on the session streams, max over ranks.  In the same run rank 0 also solves the whole
+    frame on its own GPU: that is the 1-GPU time the speed-up is quoted against, and the bits every
+    strip must reproduce (CRC32 of every rank's rows against the same rows of the 1-GPU result).
+    Collective: every rank calls it.  Returns the block on rank 0, None elsewhere."""
+    import zlib
+    from jpeg2png_b200 import abi, strips, synth
+    W, H, it = STRONG['width'], STRONG['height'], STRONG['iterations']
+    base = synth.synth_coefs(-(-W // 64) * 16, -(-H // 64) * 16, STRONG['quality'], STRONG['subsampling'], STRONG['seed'])
+    img = synth.tile_coefs(base, 4, 4, W, H)     # a quarter-size cartoon tiled 4x4 at block level: seconds of host time, same statistics
+    mcu = 8 * max(p.h_samp for p in img.planes)
+    plan = strips.plan_strips(img.frame_h, mcu, world)
+    dev = torch.device('cuda', local_rank)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    # ---- the whole frame on one GPU (rank 0) ------------------------------------------------
+    single_ms, ref_crcs = None, None
+    if rank == 0:
+        d = abi.FrameDesc()
+        d.nchannel = 3
+        for c, p in enumerate(img.planes):
+            d.plane_w[c], d.plane_h[c], d.w_samp[c], d.h_samp[c] = p.w, p.h, p.w_samp, p.h_samp
+            d.pweight[c] = PWEIGHT
+        d.weight = WEIGHT
+        d.iterations = it
+        s = C.c_void_p()
+        if lib.j2p_session_create(C.byref(s), local_rank, C.byref(d)) != 0:
+            raise RuntimeError(lib.j2p_last_error().decode())
+        for c, p in enumerate(img.planes):
+            data, quant = np.ascontiguousarray(p.data), np.ascontiguousarray(p.quant)
+            if lib.j2p_session_upload(s, c, data.ctypes.data, quant.ctypes.data, None) != 0:
+                raise RuntimeError(lib.j2p_last_error().decode())
+        stream = torch.cuda.ExternalStream(lib.j2p_session_stream(s), device=dev)
+        for _ in range(2):
+            lib.j2p_session_iterate(s, 0, 10)                      # warm-up
+        lib.j2p_session_sync(s)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        if lib.j2p_session_iterate(s, 0, it) != 0:
+            raise RuntimeError(lib.j2p_last_error().decode())
+        e1.record(stream)
+        lib.j2p_session_sync(s)
+        single_ms = e0.elapsed_time(e1)
+        ref_crcs = []
+        for c in range(3):
+            out = np.empty((img.frame_h, img.frame_w), np.float32)
+            lib.j2p_session_download(s, c, out.ctypes.data)
+            ref_crcs.append([zlib.crc32(out[r0:r0 + rows].tobytes()) for r0, rows in plan])
+        lib.j2p_session_destroy(s)
+    if world == 1:
+        pix = W * H * it
+        return {'workload': f"{W}x{H} Q{STRONG['quality']} {STRONG['subsampling']} synthetic JPEG coefficients, joint 3 planes, {it} iterations",
+                'n_gpus': 1, 'us_per_iteration': single_ms / it * 1e3, 'mpix_it_s': pix / (single_ms * 1e-3) / 1e6,
+                'single_gpu_us_per_iteration': single_ms / it * 1e3, 'speedup_vs_1gpu': 1.0}
+
+    # ---- the same frame in `world` row strips -----------------------------------------------
+    barrier()
+    row0, rows = plan[rank]
+    be = strips.ProductStrip(lib, img, WEIGHT, [PWEIGHT] * 3, it, row0, rows, local_rank)
+    comm = strips.native_comm(be, dist, rank, world)
+    strips.solve_strips_native(be, comm, 5)                         # warm-up: binds the peer memory, first-use costs
+    lib.j2p_session_sync(be.s)
+    barrier()
+    if lib.j2p_session_reset(be.s) != 0:
+        raise RuntimeError(lib.j2p_last_error().decode())
+    lib.j2p_session_sync(be.s)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(be.stream)
+    strips.solve_strips_native(be, comm, it)
+    e1.record(be.stream)
+    lib.j2p_session_sync(be.s)
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    strip_ms = float(t.item())
+    status = int(lib.j2p_comm_status(comm))
+    protocol = int(lib.j2p_comm_protocol(comm))
+    crcs = [zlib.crc32(be.download(c).tobytes()) for c in range(3)]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (crcs, status))
+    lib.j2p_comm_destroy(comm)
+    be.close()
+    barrier()
+    if rank != 0:
+        return None
+    same = all(gathered[r][0][c] == ref_crcs[c][r] for r in range(world) for c in range(3))
+    pix = W * H * it
+    return {'workload': f"{W}x{H} Q{STRONG['quality']} {STRONG['subsampling']} synthetic JPEG coefficients, joint 3 planes, {it} iterations, "
+                        f'ONE frame in {world} MCU-aligned row strips',
+            'n_gpus': world, 'us_per_iteration': strip_ms / it * 1e3, 'mpix_it_s': pix / (strip_ms * 1e-3) / 1e6,
+            'single_gpu_us_per_iteration': single_ms / it * 1e3, 'speedup_vs_1gpu': single_ms / strip_ms,
+            'protocol': 'peer memory: both exchanges inside the solver kernels (NVLink stores + flags)' if protocol == 1 else 'NCCL all-gather + send/recv between the kernels',
+            'exchange_status': 'ok' if all(g[1] == 0 for g in gathered) else 'TIMEOUT',
+            'bit_identical_to_1gpu': bool(same),
+            'timing': 'CUDA events on the session streams, max over ranks; the 1-GPU time is rank 0 solving the whole frame in the same run'}
 
 
 def device_decode(lib, img, device):

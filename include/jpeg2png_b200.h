@@ -90,6 +90,14 @@ const char *j2p_last_error(void);
 /* Number of CUDA devices visible to this process (0 if none / no driver). */
 int j2p_device_count(void);
 
+/* Which device the drop-in compute() uses when called from THIS host thread (the reference's
+ * compute() has no device argument, compute.h:8).  -1 (the initial state of every thread) = the
+ * process default: environment J2P_DEVICE, else device 0.  The reference calls compute() from
+ * OpenMP threads for the three planes (jpeg2png.c:147-152) and for files (jpeg2png.c:330); a host
+ * that binds each of those threads to its own device spreads them over the GPUs of the box. */
+int j2p_set_thread_device(int device);
+int j2p_thread_device(void);
+
 /* Describes one frame to solve: the planes that are optimised TOGETHER (reference joint mode:
  * nchannel = 3, jpeg2png.c:144; separate mode: three sessions with nchannel = 1, :147-152).
  * A horizontal strip of the frame (multi-GPU spatial tiling) is selected at creation time with

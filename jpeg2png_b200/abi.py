@@ -123,6 +123,10 @@ def declare_product(lib: C.CDLL) -> C.CDLL:
     lib.j2p_last_error.argtypes = []
     lib.j2p_device_count.restype = C.c_int
     lib.j2p_device_count.argtypes = []
+    lib.j2p_set_thread_device.restype = C.c_int
+    lib.j2p_set_thread_device.argtypes = [C.c_int]
+    lib.j2p_thread_device.restype = C.c_int
+    lib.j2p_thread_device.argtypes = []
     lib.j2p_session_create.restype = C.c_int
     lib.j2p_session_create.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(FrameDesc)]
     lib.j2p_session_create_strip.restype = C.c_int
@@ -195,7 +199,7 @@ HEADER_SYMBOLS = [
     'j2p_session_width', 'j2p_session_height', 'j2p_session_upload', 'j2p_session_reset',
     'j2p_session_iterate', 'j2p_session_profile', 'j2p_session_wait_iteration', 'j2p_session_download', 'j2p_session_set_logging',
     'j2p_session_objective', 'j2p_session_sync', 'j2p_session_stream', 'j2p_session_plane_ptr',
-    'j2p_session_launches', 'j2p_version', 'j2p_host_prefault',
+    'j2p_session_launches', 'j2p_version', 'j2p_host_prefault', 'j2p_set_thread_device', 'j2p_thread_device',
 ]
 
 _product = None

@@ -20,9 +20,11 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #ifdef _OPENMP
 #include <omp.h>
-#include <time.h>
+#else
+static int omp_get_thread_num(void) { return 0; }
 #endif
 
 #include "../../include/jpeg2png_b200.h"

@@ -92,10 +92,8 @@ void compute(unsigned nchannel, struct coef *coefs, struct logger *log, struct p
                 d.pweight[c] = pweight[c];
         }
 
-        /* device choice: J2P_DEVICE (set by the batch / multi-GPU drivers), default 0 */
-        int device = 0;
-        const char *env = getenv("J2P_DEVICE");
-        if (env && *env) device = atoi(env);
+        /* device choice: this thread's binding (j2p_set_thread_device), else J2P_DEVICE, else 0 */
+        const int device = j2p_thread_device();
 
         const char *trace_env = getenv("J2P_TRACE");
         const int trace = trace_env && *trace_env == '1';

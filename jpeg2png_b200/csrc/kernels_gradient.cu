@@ -14,7 +14,9 @@
 // block-local 8-point butterflies in emulated-reference arithmetic (numerics.cuh).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
+#include "gradient_common.cuh"
 #include "kernels.cuh"
 #include "numerics.cuh"
 
@@ -44,68 +46,6 @@ namespace j2p {
 // and sources whose norm is 0 (compute.c:97, :158), contribute nothing: their shared reciprocal
 // is set to 0, which makes every quotient of that pixel exactly 0.
 // ------------------------------------------------------------------------------------------
-constexpr int GM_WARPS = 4, GM_NT = GM_WARPS * 32, GM_USE = 60;
-#ifndef J2P_GRAD_MIN_CTAS
-#define J2P_GRAD_MIN_CTAS 3     // resident CTAs per SM the register allocation is bounded for (4 spills: measured slower)
-#endif
-
-// IEEE fallbacks of the two quotient stages, for rows the guards reject (numerics.cuh).  Out of line
-// and fed through local memory on purpose: they run once in millions of rows, and kept inline they
-// cost the hot path register copies at every row.
-template <int NC>
-struct TvSlow {
-    float gx[NC][2], gy[NC][2];     // in: forward differences of the source row
-    float q[3][NC][2];              // out: self / right / below quotients (compute.c:98-103)
-    float n[2];                     // out: the norms (for the objective log)
-};
-// A value read back from local memory after the fallback call is passed through one ALU
-// instruction inside the cold branch.  Without it the first instruction after the join waits on
-// the scoreboard the compiler gave those local loads — the same one the row prefetch uses — and
-// every row stalls there until its prefetch has landed (15 % of all stall samples, 5 us per 4K
-// iteration; profiles/r01_notes.md).  `zero` is 0, but not to the compiler.
-__device__ __forceinline__ float settle(float v, unsigned zero) { return __uint_as_float(__float_as_uint(v) ^ zero); }
-template <int NC>
-__device__ __noinline__ void tv_slow(TvSlow<NC> *io, float a1, bool src_in) {
-    for (int k = 0; k < 2; k++) {
-        float ssq = 0.f;
-        for (int c = 0; c < NC; c++) ssq = fadd(fadd(ssq, fsq(io->gx[c][k])), fsq(io->gy[c][k]));   // compute.c:84-89
-        const float n = fsqrt(ssq);
-        const bool live = src_in && n != 0.f;                                                       // compute.c:97
-        io->n[k] = n;
-        for (int c = 0; c < NC; c++) {
-            const float gx = io->gx[c][k], gy = io->gy[c][k];
-            io->q[0][c][k] = live ? fdiv(fmul(a1, -fadd(gx, gy)), n) : 0.f;
-            io->q[1][c][k] = live ? fdiv(fmul(a1, gx), n) : 0.f;
-            io->q[2][c][k] = live ? fdiv(fmul(a1, gy), n) : 0.f;
-        }
-    }
-}
-template <int NC>
-struct TgvSlow {
-    float gxx[NC][2], gyy[NC][2], sym[NC][2];   // in: second differences of the source row
-    float q[4][NC][2];                          // out: a2 * (self / left-right / up-down / diagonal quotients) (compute.c:165-182)
-    float n[2];
-};
-template <int NC>
-__device__ __noinline__ void tgv_slow(TgvSlow<NC> *io, float a2, bool src_in) {
-    for (int k = 0; k < 2; k++) {
-        float ssq = 0.f;
-        for (int c = 0; c < NC; c++)
-            ssq = fadd(ssq, fadd(fadd(fsq(io->gxx[c][k]), fmul(2.f, fsq(io->sym[c][k]))), fsq(io->gyy[c][k])));   // compute.c:148-152
-        const float n = fsqrt(ssq);
-        const bool live = src_in && n != 0.f;                                                       // compute.c:158
-        io->n[k] = n;
-        for (int c = 0; c < NC; c++) {
-            const float gxx = io->gxx[c][k], gyy = io->gyy[c][k], sym = io->sym[c][k];
-            const float self = -fadd(fadd(fmul(2.f, gxx), fmul(2.f, sym)), fmul(2.f, gyy));
-            io->q[0][c][k] = live ? fmul(a2, fdiv(self, n)) : 0.f;
-            io->q[1][c][k] = live ? fmul(a2, fdiv(fadd(sym, gxx), n)) : 0.f;
-            io->q[2][c][k] = live ? fmul(a2, fdiv(fadd(gyy, sym), n)) : 0.f;
-            io->q[3][c][k] = live ? fmul(a2, fdiv(-sym, n)) : 0.f;
-        }
-    }
-}
-
 // LOG: additionally sum the objective terms the reference logs (compute.c:91,155: tv += alpha*norm
 // per pixel, fp64) — only instantiated for sessions with logging enabled (-c csv).
 template <int NC, bool LOG, bool TGV>
@@ -489,13 +429,12 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient(const __g
 // host-side launcher
 // ------------------------------------------------------------------------------------------
 // Band height: one resident wave of CTAs if the frame allows it (long bands amortise the two
-// extra source rows each band recomputes), never fewer than 8 rows per band.
-static int g_grad_slots = 0;   // CTAs resident on the whole device, set by configure_kernels()
-
-void grad_geometry(int W, int H, int *ctas_x, int *bands, int *band_rows) {
+// extra source rows each band recomputes), never fewer than 8 rows per band.  `slots` = CTAs of
+// the gradient kernel resident on the session's device at once (FrameDev::grad_slots).
+void grad_geometry(int W, int H, int slots, int *ctas_x, int *bands, int *band_rows) {
     const int strips = (W + GM_USE - 1) / GM_USE;
     *ctas_x = (strips + GM_WARPS - 1) / GM_WARPS;
-    const int slots = g_grad_slots > 0 ? g_grad_slots : 148 * 3;
+    if (slots <= 0) slots = 148 * 3;
     int want = slots / *ctas_x;
     if (want < 1) want = 1;
     int rows = (H + want - 1) / want;
@@ -511,8 +450,14 @@ int grad_cta_count(int W, int H) {
 }
 
 cudaError_t configure_project_kernels();
+int packed_gradient_occupancy();
+cudaError_t launch_gradient_packed(const FrameDev &F, float factor, cudaStream_t s);
 
-cudaError_t configure_kernels() {
+// J2P_GRAD_SCALAR=1: the scalar kernel for every session (A/B aid; it is always the -c csv build)
+static bool g_grad_scalar = false;
+
+// once per device and process; *slots = resident CTAs of the gradient kernel on the current device
+cudaError_t configure_kernels(int *slots) {
     int per_sm = 0, dev = 0, sms = 0;
     cudaError_t e = configure_project_kernels();
     if (e != cudaSuccess) return e;
@@ -520,9 +465,15 @@ cudaError_t configure_kernels() {
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gradient<3, false, true>, GM_NT, 0);
-    if (e != cudaSuccess) return e;
-    g_grad_slots = sms * (per_sm > 0 ? per_sm : 1);
+    const char *env = getenv("J2P_GRAD_SCALAR");
+    g_grad_scalar = env && *env == '1';
+    if (g_grad_scalar) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gradient<3, false, true>, GM_NT, 0);
+        if (e != cudaSuccess) return e;
+    } else {
+        per_sm = packed_gradient_occupancy();
+    }
+    *slots = sms * (per_sm > 0 ? per_sm : 1);
     return cudaSuccess;
 }
 
@@ -536,8 +487,9 @@ static void launch_gradient_nc(const FrameDev &F, float factor, dim3 grid, int r
 }
 
 cudaError_t launch_gradient(const FrameDev &F, float factor, cudaStream_t s) {
+    if (!F.log_on && !g_grad_scalar) return launch_gradient_packed(F, factor, s);
     int cx, bands, rows;
-    grad_geometry(F.W, F.t1 - F.t0, &cx, &bands, &rows);
+    grad_geometry(F.W, F.t1 - F.t0, F.grad_slots, &cx, &bands, &rows);
     const dim3 grid(cx, bands);
     if (F.log_on) {
         if (F.use_tgv) launch_gradient_nc<true, true>(F, factor, grid, rows, s);

@@ -1,0 +1,435 @@
+// kernels_gradient_packed.cu — the production sub-gradient kernel: k_gradient on packed fp32.
+//
+// Same algorithm, same order of IEEE operations and therefore the same bits as the scalar
+// k_gradient of kernels_gradient.cu (which stays as the objective-logging build): FISTA point
+// (compute.c:431-440), TV (compute.c:73-113) and second-order TGV (compute.c:128-186) sub-gradient
+// as an ordered per-pixel gather, the DCT-distance term from `gp`, per-CTA fp64
+// sums of g^2 and the last-CTA fold into the norms of compute.c:200-206.
+//
+// What changed is how the arithmetic is issued.  The scalar kernel is bound by instruction issue
+// (profiles/r01_ncu_full_k_gradient.txt: 117 M warp instructions at 4K, 74 % issue-active, 62 % of
+// them fp32 FADD/FMUL/FFMA).  A lane owns two adjacent columns and runs the identical sequence on
+// both, so here the two columns live in one 64-bit register pair and every fp32 operation is ONE
+// FADD2 / FMUL2 / FFMA2 (add/mul/fma.rn.f32x2): bit-identical per half, same fp32-pipe time, half
+// the issue slots (profiles/r02_microbench3_packed_fp32.txt).  On top of that:
+//   * the row-to-row state is ping-ponged between two register sets by unrolling two row steps
+//     with swapped roles, which removes the ~45 register copies per row of the scalar kernel;
+//   * the DCT-distance term enters as fma(gp, mask, 0) — one instruction that is both the
+//     "0 + gp" of compute.c:62 and the validity select;
+//   * dead sources are made harmless before the square root (norm^2 := 1, reciprocal := 0) instead
+//     of after it, which halves the selects per pixel;
+//   * for strip sessions the two exchanges of an iteration are part of the kernel (strip_sync.cuh).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gradient_common.cuh"
+#include "kernels.cuh"
+#include "numerics.cuh"
+#include "strip_sync.cuh"
+
+namespace j2p {
+
+// what one row step hands to the next; f2 = the lane's two adjacent columns
+template <int NC>
+struct RowCarry {
+    f2 y[NC];            // FISTA point of the newest row
+    f2 gx[NC], gy[NC];   // forward differences of the newest source row
+    f2 og[NC];           // gradient of the newest target row after its first nine addends
+    f2 tvb[NC];          // its TV "below" quotients   (addend 1 of the next target row)
+    f2 ud[NC], dg[NC];   // its TGV "above/below" and diagonal quotients (addends 4, 5 of the next target row)
+    bool ok1, ok2;       // row guard (numerics.cuh) of the newest and the second newest row
+};
+
+__device__ __forceinline__ f2 shl_from_left(f2 v, float from_left) { return pk(from_left, lo(v)); }    // (left neighbour's hi, own lo)
+__device__ __forceinline__ f2 shr_from_right(f2 v, float from_right) { return pk(hi(v), from_right); } // (own hi, right neighbour's lo)
+
+// GPM: how the DCT-distance term is addressed.  1 = every plane is full resolution and covers the
+// whole frame (4:4:4): gp has the frame's geometry, one 8-byte load per plane at the pixel offset.
+// 0 = generic (any sampling factors, grids smaller than the frame).
+template <int NC, bool TGV, int GPM>
+__global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient_packed(const __grid_constant__ FrameDev F, const float factor, const int band_rows) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int W = F.W, H = F.H;
+    const int X0 = (blockIdx.x * GM_WARPS + wid) * GM_USE;   // first target column of this warp
+    const int yb = F.t0 + blockIdx.y * band_rows;            // first target row of this CTA (local row index)
+    const int ye = min(yb + band_rows, F.t1);
+    const int s_first = -F.y0g;                              // local index of the frame's first row
+    const int px0 = X0 - 2 + 2 * lane;                       // even; W is even => the pair is in or out together
+    const bool pair_in = px0 >= 0 && px0 < W;
+    const bool is_target = pair_in && lane >= 1 && lane <= 30;
+    const bool has_l0 = px0 > 0, has_r1 = px0 + 1 < W - 1;   // hi always has a left neighbour, lo a right one
+    const f2 a1s = splat(F.a1), a1n = splat(-F.a1), a2s = splat(F.a2), a2n = splat(-F.a2), a2m2 = splat(fmul(-2.f, F.a2));
+    const f2 fac = splat(factor), half2 = splat(0.5f), zero2 = 0ull;
+    const f2 one = splat(F.one);                             // see addm2(): sums with a product go through fma(m, one, b)
+    const unsigned zero = (unsigned)band_rows >> 31;         // see settle()
+
+    // strip sessions: the halo rows of x_k arrive from the neighbours' projection (strip_sync.cuh)
+    strip_wait_halo(F.sync, blockIdx.y == 0, blockIdx.y == gridDim.y - 1);
+
+    double acc[NC];
+    RowCarry<NC> A, B;
+    float2 ldx[NC], ldp[NC];      // x_k / x_{k-1} of the row after the one being formed
+    f2 pgp[NC];                   // DCT-distance term of the next target row (raw)
+    f2 gmask[NC];                 // 1 where the pixel has such a term, else 0 (compute.c:58-62 footprint, pweight != 0)
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        acc[c] = 0.;
+        ldx[c] = ldp[c] = make_float2(0.f, 0.f);
+        A.y[c] = A.gx[c] = A.gy[c] = A.og[c] = A.tvb[c] = A.ud[c] = A.dg[c] = zero2;
+        pgp[c] = zero2;
+    }
+    A.ok1 = A.ok2 = true;
+
+    // column part of the gp addressing
+    int gpx[NC][2];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        float m[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int cx = GPM == 1 ? px0 + k : (px0 + k) / F.pl[c].sw;
+            const bool has = F.pl[c].use_prob && pair_in && cx < F.pl[c].cw;
+            gpx[c][k] = has ? cx : 0;
+            m[k] = has ? 1.f : 0.f;
+        }
+        gmask[c] = pk(m[0], m[1]);
+    }
+
+    // Rows/columns outside the frame are never consumed (their sources are dead), so the loads are
+    // made unconditional by clamping the address into the frame: no branches.
+    const int pxc = pair_in ? px0 : 0;
+    auto issue_row_loads = [&](int row) {
+        const int rc = min(max(row, 0), H - 1);
+        const unsigned gi = (unsigned)rc * (unsigned)W + (unsigned)pxc;   // frames are far below 2^32 pixels (checked at session creation)
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            ldx[c] = *reinterpret_cast<const float2 *>(F.pl[c].x + gi);
+            ldp[c] = *reinterpret_cast<const float2 *>(F.pl[c].xp + gi);
+        }
+    };
+    // coefficient-grid row of the next target row, tracked incrementally (no per-step division)
+    int gcy[NC], grem[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        const int r0 = yb - F.t0;                   // coefficient rows are stored from the first owned row
+        gcy[c] = GPM == 1 ? r0 : r0 / F.pl[c].sh;
+        grem[c] = GPM == 1 ? 0 : r0 - gcy[c] * F.pl[c].sh;
+    }
+    unsigned gp_rows_ok = 0;            // bit c: the prefetched gp row exists
+    auto issue_gp_loads = [&](int row) {   // for target rows yb, yb+1, ... in order; raw loads only
+        if (GPM == 1) {                     // gp has the frame's geometry and every target row has its gp row
+            const unsigned gi = (unsigned)(row - F.t0) * (unsigned)W + (unsigned)pxc;
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                const float2 v = *reinterpret_cast<const float2 *>(F.pl[c].gp + gi);
+                pgp[c] = pk(v.x, v.y);
+            }
+            return;
+        }
+        gp_rows_ok = 0;
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            const PlaneDev &P = F.pl[c];
+            const bool rowok = gcy[c] < P.ch;
+            const float *gr = P.gp + (size_t)(rowok ? gcy[c] : 0) * P.cw;
+            pgp[c] = pk(gr[gpx[c][0]], gr[gpx[c][1]]);
+            if (++grem[c] == P.sh) { grem[c] = 0; gcy[c]++; }
+            if (rowok) gp_rows_ok |= 1u << c;
+        }
+    };
+
+    // One row step: the FISTA point of row i is formed, source row s = i-1 gets its TV and TGV
+    // quotients, target row s-1 its last two addends (and is stored), target row s its first nine.
+    // P: the carry of the previous step (read), N: the carry this step leaves (written).
+    auto row_step = [&](const int i, const RowCarry<NC> &P, RowCarry<NC> &N) {
+        // ---- FISTA point of row i (compute.c:436) from the loads issued one step ago -----------
+        unsigned ykey = 0xffffffffu;
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            const f2 x = pk(ldx[c].x, ldx[c].y), xp = pk(ldp[c].x, ldp[c].y);
+            N.y[c] = addm2(mul2(fac, sub2(x, xp)), x, one);
+            ykey = min(ykey, min(qdiv_key(lo(N.y[c])), qdiv_key(hi(N.y[c]))));
+        }
+        const bool ok0 = !__any_sync(0xffffffffu, ykey < QDIV_YKEY_MIN);    // one guard per VALUE (numerics.cuh, "row guard")
+        N.ok1 = ok0;
+        N.ok2 = P.ok1;
+        // the DCT-distance addend of target row s: 0 + gp where the pixel has one (compute.c:62), else 0
+        f2 pterm[NC];
+#pragma unroll
+        for (int c = 0; c < NC; c++) pterm[c] = fma2(pgp[c], GPM == 1 || ((gp_rows_ok >> c) & 1u) ? gmask[c] : zero2, zero2);
+        issue_row_loads(i + 1);                                 // clamped: the rows too many at the end are harmless
+        if (i >= yb && i < ye) issue_gp_loads(i);               // consumed next step, where the target row is s = i
+
+        const int s = i - 1;
+        const bool src_in = pair_in && s >= 0 && s < H;
+        // No row below the frame's last row: gy := 0 (compute.c:81).  Nothing to do for it: the row
+        // loads are clamped into the buffer, whose last row IS the frame's last row whenever that
+        // row is reachable, so row s+1 re-reads row s and gy comes out +0.
+
+        // ---- source row s: TV (compute.c:79-105) -------------------------------------------
+        f2 gx0[NC], gy0[NC], tvs0[NC], tvr0[NC];
+        f2 n1 = zero2;
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            float yr1 = __shfl_down_sync(0xffffffffu, lo(P.y[c]), 1);
+            yr1 = has_r1 ? yr1 : hi(P.y[c]);                    // no right neighbour: gx := 0 (compute.c:79)
+            gx0[c] = sub2(shr_from_right(P.y[c], yr1), P.y[c]);
+            gy0[c] = sub2(N.y[c], P.y[c]);
+            const f2 sx = mul2(gx0[c], gx0[c]), sy = mul2(gy0[c], gy0[c]);
+            n1 = c == 0 ? addm2(sy, sx, one) : addm2(sy, addm2(sx, n1, one), one);   // 0 + gx^2 == gx^2: squares are never -0
+            N.gx[c] = gx0[c];
+            N.gy[c] = gy0[c];
+        }
+        {
+            const bool l0 = src_in && lo(n1) != 0.f, l1 = src_in && hi(n1) != 0.f;   // sqrtf(x) != 0  <=>  x != 0   (compute.c:97)
+            const f2 ss = pk(l0 ? lo(n1) : 1.f, l1 ? hi(n1) : 1.f);                  // dead source: norm 1, reciprocal 0 => every quotient exactly 0
+            const bool fast = ok0 && P.ok1 && !__any_sync(0xffffffffu, !root_arg_ok(lo(ss)) || !root_arg_ok(hi(ss)));
+            if (__builtin_expect(fast, true)) {
+                const f2 n = sqrt2_core(ss), nb = neg2(n);
+                const f2 yr = rcp2_core(n, nb);
+                const f2 y = pk(l0 ? lo(yr) : 0.f, l1 ? hi(yr) : 0.f);
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    tvs0[c] = qdiv2(mul2(a1n, add2(gx0[c], gy0[c])), nb, y);   // compute.c:98: (a1 * -(gx+gy)) / n
+                    tvr0[c] = qdiv2(mul2(a1s, gx0[c]), nb, y);                  // compute.c:100
+                    N.tvb[c] = qdiv2(mul2(a1s, gy0[c]), nb, y);                 // compute.c:103
+                }
+            } else {                                                    // outside the proven range: IEEE square root and division
+                TvSlow<NC> io;
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    io.gx[c][0] = lo(gx0[c]); io.gx[c][1] = hi(gx0[c]);
+                    io.gy[c][0] = lo(gy0[c]); io.gy[c][1] = hi(gy0[c]);
+                }
+                tv_slow<NC>(&io, F.a1, src_in);
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    tvs0[c] = pk(settle(io.q[0][c][0], zero), settle(io.q[0][c][1], zero));
+                    tvr0[c] = pk(settle(io.q[1][c][0], zero), settle(io.q[1][c][1], zero));
+                    N.tvb[c] = pk(settle(io.q[2][c][0], zero), settle(io.q[2][c][1], zero));
+                }
+            }
+        }
+
+        // ---- target row s: addends 1..6 (DCT distance; TV above, left, self; TGV above, above-right)
+        f2 oA[NC];
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            const float tvr_l = __shfl_up_sync(0xffffffffu, hi(tvr0[c]), 1);
+            f2 o = add2(add2(add2(pterm[c], P.tvb[c]), shl_from_left(tvr0[c], tvr_l)), tvs0[c]);
+            if (TGV) {
+                const float dg_r = __shfl_down_sync(0xffffffffu, lo(P.dg[c]), 1);
+                o = add2(addm2(P.ud[c], o, one), shr_from_right(P.dg[c], dg_r));
+            }
+            oA[c] = o;
+        }
+
+        // ---- source row s: second-order TGV (compute.c:136-183) ----------------------------
+        f2 t2s0[NC], lr0[NC];
+        if (TGV) {
+            f2 gyPv[NC];
+#pragma unroll
+            for (int c = 0; c < NC; c++) gyPv[c] = P.gy[c];
+            if (__builtin_expect(s <= s_first, false)) {     // no row above in the frame: gxy, gyy := 0 (compute.c:141-143)
+                // gxy needs no help: the clamped loads made "row -1" a copy of row 0, so the gx carried
+                // from the previous step already equals gx0.  gy of that copy is 0, not gy0.
+#pragma unroll
+                for (int c = 0; c < NC; c++) gyPv[c] = gy0[c];
+            }
+            f2 gxx[NC], gyy[NC], sym[NC];
+            f2 n2 = zero2;
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                float gxl = __shfl_up_sync(0xffffffffu, hi(gx0[c]), 1);
+                float gyl = __shfl_up_sync(0xffffffffu, hi(gy0[c]), 1);
+                gxl = has_l0 ? gxl : lo(gx0[c]);            // no left neighbour: gxx, gyx := 0 (compute.c:137-139)
+                gyl = has_l0 ? gyl : lo(gy0[c]);
+                gxx[c] = sub2(gx0[c], shl_from_left(gx0[c], gxl));
+                const f2 gyx = sub2(gy0[c], shl_from_left(gy0[c], gyl));
+                const f2 gxy = sub2(gx0[c], P.gx[c]);
+                gyy[c] = sub2(gy0[c], gyPv[c]);
+                const f2 u = add2(gxy, gyx);
+                sym[c] = mul2(u, half2);                    // (gxy+gyx)/2., exact either way
+                // 2*sym^2 as u*sym: 2*RN((u/2)^2) == RN(u*(u/2)) (power-of-two scalings commute with rounding
+                // while nothing underflows; rows where that is not guaranteed are flagged by the row guard
+                // and recompute n2 in the reference's form in tgv_slow)
+                const f2 t = addm2(mul2(gyy[c], gyy[c]), addm2(mul2(u, sym[c]), mul2(gxx[c], gxx[c]), one), one);
+                n2 = c == 0 ? t : add2(n2, t);              // 0 + t == t: t is never -0
+            }
+            const bool l0 = src_in && lo(n2) != 0.f, l1 = src_in && hi(n2) != 0.f;   // compute.c:158
+            const f2 ss = pk(l0 ? lo(n2) : 1.f, l1 ? hi(n2) : 1.f);
+            const bool fast = ok0 && P.ok1 && P.ok2 && !__any_sync(0xffffffffu, !root_arg_ok(lo(ss)) || !root_arg_ok(hi(ss)));
+            if (__builtin_expect(fast, true)) {
+                const f2 n = sqrt2_core(ss), nb = neg2(n);
+                const f2 yr = rcp2_core(n, nb);
+                const f2 y = pk(l0 ? lo(yr) : 0.f, l1 ? hi(yr) : 0.f);
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    // compute.c:165: a2 * (-(2gxx + 2s + 2gyy) / n) == (-2 a2) * (((s + gxx) + gyy) / n): doubling
+                    // commutes with every rounding involved (no overflow in this range)
+                    const f2 sx = addm2(sym[c], gxx[c], one);
+                    t2s0[c] = mul2(a2m2, qdiv2(add2(sx, gyy[c]), nb, y));
+                    lr0[c] = mul2(a2s, qdiv2(sx, nb, y));                           // compute.c:167,170
+                    N.ud[c] = mul2(a2s, qdiv2(addm2(sym[c], gyy[c], one), nb, y));        // compute.c:173,176
+                    N.dg[c] = mul2(a2n, qdiv2(sym[c], nb, y));                      // compute.c:179,182: a2 * (-s / n)
+                }
+            } else {
+                TgvSlow<NC> io;
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    io.gxx[c][0] = lo(gxx[c]); io.gxx[c][1] = hi(gxx[c]);
+                    io.gyy[c][0] = lo(gyy[c]); io.gyy[c][1] = hi(gyy[c]);
+                    io.sym[c][0] = lo(sym[c]); io.sym[c][1] = hi(sym[c]);
+                }
+                tgv_slow<NC>(&io, F.a2, src_in);
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    t2s0[c] = pk(settle(io.q[0][c][0], zero), settle(io.q[0][c][1], zero));
+                    lr0[c] = pk(settle(io.q[1][c][0], zero), settle(io.q[1][c][1], zero));
+                    N.ud[c] = pk(settle(io.q[2][c][0], zero), settle(io.q[2][c][1], zero));
+                    N.dg[c] = pk(settle(io.q[3][c][0], zero), settle(io.q[3][c][1], zero));
+                }
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < NC; c++) t2s0[c] = lr0[c] = N.ud[c] = N.dg[c] = zero2;
+        }
+
+        // ---- target row s-1: last two addends (TGV below-left, below), store, sum of squares ----
+        if (i >= yb + 2 && i <= ye + 1) {
+            f2 o[NC];
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                o[c] = P.og[c];
+                if (TGV) {
+                    const float dgl = __shfl_up_sync(0xffffffffu, hi(N.dg[c]), 1);
+                    o[c] = addm2(N.ud[c], add2(o[c], shl_from_left(N.dg[c], dgl)), one);
+                }
+            }
+            if (is_target) {
+                const unsigned gi = (unsigned)(s - 1) * (unsigned)W + (unsigned)px0;
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    *reinterpret_cast<float2 *>(F.pl[c].g + gi) = make_float2(lo(o[c]), hi(o[c]));
+                    const f2 sq = mul2(o[c], o[c]);
+                    acc[c] = __dadd_rn(acc[c], (double)lo(sq));       // compute.c:203
+                    acc[c] = __dadd_rn(acc[c], (double)hi(sq));
+                }
+            }
+        }
+
+        // ---- target row s: addends 7..9 (TGV left, self, right of this row's quotients) ----------
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            f2 o = oA[c];
+            if (TGV) {
+                const float lr_l = __shfl_up_sync(0xffffffffu, hi(lr0[c]), 1);
+                const float lr_r = __shfl_down_sync(0xffffffffu, lo(lr0[c]), 1);
+                o = add2(addm2(t2s0[c], add2(o, shl_from_left(lr0[c], lr_l)), one), shr_from_right(lr0[c], lr_r));
+            }
+            N.og[c] = o;
+        }
+    };
+
+    // Warps whose strip starts beyond the frame (only in the last CTA column of odd widths) run the
+    // same loop on clamped loads and store nothing: control flow depends on block indices and kernel
+    // parameters only, so every shuffle is executed convergently.  Two row steps per trip with the
+    // roles of the two carries swapped; an odd row count gets one idle step at the end (its loads
+    // are clamped, its store is suppressed by the row test inside the step).
+    issue_row_loads(yb - 2);
+    for (int i = yb - 2; i <= ye + 1; i += 2) {
+        row_step(i, A, B);
+        row_step(i + 1, B, A);
+    }
+
+    // CTA reduction (fixed order => run-to-run deterministic), then the last-CTA fold
+    __shared__ double red[3][GM_WARPS];
+    __shared__ double fin[3];
+    __shared__ unsigned ticket;
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        const double sum = warp_sum(acc[c]);
+        if (lane == 0) red[c][wid] = sum;
+    }
+    __syncthreads();
+    const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x, ncta = gridDim.x * gridDim.y;
+    if (tid < NC) {
+        double sum = 0.;
+        for (int k = 0; k < GM_WARPS; k++) sum = __dadd_rn(sum, red[tid][k]);
+        F.partials[(size_t)tid * F.grad_ctas + cta] = sum;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) ticket = atomicAdd(F.counter, 1u);
+    __syncthreads();
+    if (ticket == ncta - 1) {
+        __threadfence();
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            double sum = 0.;
+            for (unsigned k = tid; k < ncta; k += GM_NT) sum = __dadd_rn(sum, __ldcg(&F.partials[(size_t)c * F.grad_ctas + k]));
+            sum = warp_sum(sum);
+            if (lane == 0) red[c][wid] = sum;
+        }
+        __syncthreads();
+        if (tid < 3) {
+            double sum = 0.;
+            if (tid < NC)
+                for (int k = 0; k < GM_WARPS; k++) sum = __dadd_rn(sum, red[tid][k]);
+            fin[tid] = sum;
+            if (tid < NC) {
+                const float norm = fsqrt(__double2float_rn(sum));                               // compute.c:205
+                F.sums[tid] = sum;                                                              // strips driven by the host / NCCL combine these
+                F.norms[tid] = norm;
+                F.norms[4 + tid] = __frcp_rn(norm);                                             // shared reciprocal for k_project
+            }
+        }
+        if (tid == 0) *F.counter = 0u;
+        if (F.sync.nranks > 1) {                                                                // strips over peer memory
+            __syncthreads();
+            strip_post_sums(F.sync, fin, tid);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side launcher (geometry shared with the scalar kernel: grad_geometry in kernels_gradient.cu)
+// ------------------------------------------------------------------------------------------
+void grad_geometry(int W, int H, int slots, int *ctas_x, int *bands, int *band_rows);
+
+template <bool TGV, int GPM>
+static void launch_packed_nc(const FrameDev &F, float factor, dim3 grid, int rows, cudaStream_t s) {
+    switch (F.nc) {
+        case 1: k_gradient_packed<1, TGV, GPM><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
+        case 2: k_gradient_packed<2, TGV, GPM><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
+        default: k_gradient_packed<3, TGV, GPM><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
+    }
+}
+
+int packed_gradient_occupancy() {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gradient_packed<3, true, 0>, GM_NT, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return per_sm;
+}
+
+cudaError_t launch_gradient_packed(const FrameDev &F, float factor, cudaStream_t s) {
+    int cx, bands, rows;
+    grad_geometry(F.W, F.t1 - F.t0, F.grad_slots, &cx, &bands, &rows);
+    const dim3 grid(cx, bands);
+    bool full = true;      // every plane at full resolution over the whole (local) frame: gp has the frame's geometry
+    for (int c = 0; c < F.nc; c++) full = full && F.pl[c].sw == 1 && F.pl[c].sh == 1 && F.pl[c].cw == F.W && F.pl[c].ch >= F.t1 - F.t0;
+    if (full) {
+        if (F.use_tgv) launch_packed_nc<true, 1>(F, factor, grid, rows, s);
+        else launch_packed_nc<false, 1>(F, factor, grid, rows, s);
+    } else {
+        if (F.use_tgv) launch_packed_nc<true, 0>(F, factor, grid, rows, s);
+        else launch_packed_nc<false, 0>(F, factor, grid, rows, s);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace j2p

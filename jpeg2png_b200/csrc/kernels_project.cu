@@ -6,6 +6,7 @@
 #include "kernels.cuh"
 #include "numerics.cuh"
 #include "project_common.cuh"
+#include "strip_sync.cuh"
 
 
 namespace j2p {
@@ -69,9 +70,8 @@ __global__ void __launch_bounds__(P_NT, (SW * SH <= 1) ? J2P_PROJ_MIN_CTAS : 2) 
         sq[0][tid] = F.q[c][tid];
         sq[1][tid] = F.qq[c][tid];
         sq[2][tid] = F.rqq[c][tid];
-    } else if (tid == 64) {
-        snorm[0] = F.norms[c];
-        snorm[1] = F.norms[4 + c];
+    } else if (tid < 96) {
+        strip_norm(F, c, snorm, tid - 64);                         // whole frame: what k_gradient left; strips: fold of every rank's sums
     }
     __syncthreads();
     Stepper stepper;
@@ -312,14 +312,16 @@ __global__ void k_init_plane(const float *fdata, float *x, float *xp, int W, int
 // ------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------
-// J2P_PROJ_TILE22=1: 2x2 planes through kernels_project_tile22.cu instead of k_project<2,2>
-// (opt-in until it has been validated on the GPU, see that file)
-static bool g_tile22 = false;
+// 2x2 planes (4:2:0 chroma) go through kernels_project_tile22.cu (coalesced staging; round 2:
+// bit-identical on the whole GPU suite, 8K 4:2:0 projection 508 -> 362 us, profiles/r02_notes.md).
+// J2P_PROJ_TILE22=0 selects the register-footprint kernel k_project<2,2> instead (A/B aid; it is
+// also what the objective-logging build uses).
+static bool g_tile22 = true;
 
 cudaError_t configure_project_kernels() {
     const char *e = getenv("J2P_PROJ_TILE22");
-    g_tile22 = e && *e == '1';
-    return g_tile22 ? configure_project_tile22() : cudaSuccess;
+    g_tile22 = !(e && *e == '0');
+    return configure_project_tile22();
 }
 
 // strip sessions: fold the per-rank sums of g^2 in rank order (deterministic), then the norms of

@@ -18,6 +18,7 @@
 #include "kernels.cuh"
 #include "numerics.cuh"
 #include "project_common.cuh"
+#include "strip_sync.cuh"
 
 namespace j2p {
 
@@ -66,9 +67,8 @@ __global__ void __launch_bounds__(PT_NT, J2P_TILE_MIN_CTAS) k_project_tile(const
         sq[0][tid] = F.q[c][tid];
         sq[1][tid] = F.qq[c][tid];
         sq[2][tid] = F.rqq[c][tid];
-    } else if (tid == 64) {
-        snorm[0] = F.norms[c];
-        snorm[1] = F.norms[4 + c];
+    } else if (tid < 96) {
+        strip_norm(F, c, snorm, tid - 64);                       // whole frame: what k_gradient left; strips: fold of every rank's sums
     }
     cp_async_wait<0>();
     __syncthreads();
@@ -187,6 +187,24 @@ __global__ void __launch_bounds__(PT_NT, J2P_TILE_MIN_CTAS) k_project_tile(const
         if (c4 < valid_c4) {
             *reinterpret_cast<float4 *>(P.xp + row0 + (size_t)row * W + (size_t)c4 * 4) = sx[row][c4 ^ row];
             if (use_prob) *reinterpret_cast<float4 *>(gp0 + (size_t)row * P.cw + (size_t)c4 * 4) = sp[row][c4 ^ row];
+        }
+    }
+
+    // ---- strips over peer memory: the strip's first / last two rows also go straight into the
+    // neighbours' halo rows (NVLink stores), and the last border CTA of the iteration raises their flag
+    const StripSync &S = F.sync;
+    if (S.nranks > 1 && S.fused_halo) {
+        const bool top = by == 0 && S.has_up, bottom = by == (int)gridDim.y - 1 && S.has_down;
+        if (top || bottom) {
+            for (int e = tid; e < 4 * PT_C4; e += PT_NT) {                // 2 rows x 64 pieces, top then bottom
+                const int side = e >> 7, r = (e >> 6) & 1, c4 = e & 63;
+                if (c4 >= valid_c4 || !(side ? bottom : top)) continue;
+                const int row = side ? 6 + r : r;
+                float *dst = (side ? S.down_dst[c] : S.up_dst[c]) + (size_t)r * W + (size_t)bx0 * 8 + (size_t)c4 * 4;
+                *reinterpret_cast<float4 *>(dst) = sx[row][c4 ^ row];
+            }
+            if (top) strip_border_done(S, 0);
+            if (bottom) strip_border_done(S, 1);
         }
     }
 }

@@ -1,10 +1,9 @@
 // kernels_project_tile22.cu — step + projection of a 2x2-subsampled plane (4:2:0 chroma) with the
 // coalesced, swizzled staging of kernels_project_tile.cu.
 //
-// STATUS: opt-in (environment J2P_PROJ_TILE22=1).  Written at the end of round 1, after the GPU
-// budget was spent; the default for 2x2 planes is still k_project<2,2> (kernels_project.cu), whose
-// threads fetch their own 64-byte row pieces.  To be validated bit for bit against it
-// (tests/test_gpu_parity.py with the variable set) and timed before it becomes the default.
+// Default for 2x2 planes since round 2 (validated bit for bit on the whole GPU suite against
+// k_project<2,2>, whose threads fetch their own 64-byte row pieces; 1080p: 56 -> 42 us per
+// projection, 8K: 508 -> 362 us; profiles/r02_notes.md).
 //
 // A coefficient block of a 2x2 plane covers 16 x 16 frame pixels.  Thread j of a block owns
 // coefficient row j = frame rows 2j and 2j+1 of that footprint (2 x 16 stepped values in
@@ -20,6 +19,7 @@
 #include "kernels.cuh"
 #include "numerics.cuh"
 #include "project_common.cuh"
+#include "strip_sync.cuh"
 
 namespace j2p {
 
@@ -73,9 +73,8 @@ __global__ void __launch_bounds__(P22_NT, 3) k_project_tile22(const __grid_const
         sq[tid] = F.q[c][tid];
         sq[64 + tid] = F.qq[c][tid];
         sq[128 + tid] = F.rqq[c][tid];
-    } else if (tid == 64) {
-        snorm[0] = F.norms[c];
-        snorm[1] = F.norms[4 + c];
+    } else if (tid < 96) {
+        strip_norm(F, c, snorm, tid - 64);                           // whole frame: what k_gradient left; strips: fold of every rank's sums
     }
     cp_async_wait<0>();
     __syncthreads();
@@ -216,6 +215,23 @@ __global__ void __launch_bounds__(P22_NT, 3) k_project_tile22(const __grid_const
         for (int i = 0; i < 8 * P22_G4 / P22_NT; i++) {
             const int e = tid + P22_NT * i, row = e / P22_G4, c4 = e % P22_G4;
             if (c4 < valid_g4) *reinterpret_cast<float4 *>(gp0 + (size_t)row * P.cw + (size_t)c4 * 4) = sgp[row * P22_G4 + (c4 ^ row)];
+        }
+    }
+
+    // ---- strips over peer memory: border rows into the neighbours' halo rows (kernels_project_tile.cu)
+    const StripSync &S = F.sync;
+    if (S.nranks > 1 && S.fused_halo) {
+        const bool top = by == 0 && S.has_up, bottom = by == (int)gridDim.y - 1 && S.has_down;
+        if (top || bottom) {
+            for (int e = tid; e < 4 * P22_C4; e += P22_NT) {             // 2 rows x 64 pieces, top then bottom
+                const int side = e / (2 * P22_C4), r = (e / P22_C4) & 1, c4 = e % P22_C4;
+                if (c4 >= valid_c4 || !(side ? bottom : top)) continue;
+                const int row = side ? 14 + r : r;
+                float *dst = (side ? S.down_dst[c] : S.up_dst[c]) + (size_t)r * W + (size_t)bx0 * 16 + (size_t)c4 * 4;
+                *reinterpret_cast<float4 *>(dst) = sx[row * P22_C4 + (c4 ^ ((row >> 1) & 7))];
+            }
+            if (top) strip_border_done(S, 0);
+            if (bottom) strip_border_done(S, 1);
         }
     }
 }

@@ -33,7 +33,7 @@
 
 namespace j2p {
 int grad_cta_count(int W, int H);
-cudaError_t configure_kernels();
+cudaError_t configure_kernels(int *slots);
 cudaError_t launch_gradient(const FrameDev &F, float factor, cudaStream_t s);
 cudaError_t launch_project(const FrameDev &F, float factor, cudaStream_t s, int *nlaunch);
 cudaError_t launch_fold_sums(const double *sums_by_rank, int nranks, int nc, float *norms, cudaStream_t s);
@@ -41,9 +41,7 @@ cudaError_t launch_decode(const int16_t *data, const float *q_host, float *out, 
 cudaError_t launch_init_plane(const float *fdata, float *x, float *xp, int W, int H, int cw, int ch, int sw, int sh,
                               cudaStream_t s);
 // kernels_strip.cu: the strip exchanges over peer memory (parameter blocks in kernels.cuh)
-cudaError_t launch_sums_exchange(const StripPeers &P, const double *my_sums, double *my_mail, unsigned *my_flag, unsigned seq, int nc,
-                                 float *norms, int *err, cudaStream_t s);
-cudaError_t launch_halo_exchange(const HaloPeers &P, unsigned seq, unsigned *ticket, int *err, cudaStream_t s);
+cudaError_t launch_halo_exchange(const HaloPeers &P, unsigned seq, unsigned *ticket, int *err, int wait_for_arrival, cudaStream_t s);
 }  // namespace j2p
 
 using namespace j2p;
@@ -76,23 +74,43 @@ constexpr int kEventRing = 32;
 struct DevCache {
     std::mutex mu;
     std::multimap<std::pair<int, size_t>, void *> blocks;
-    size_t held = 0;
-    static constexpr size_t kCap = (size_t)24 << 30;                   // bytes kept at most; beyond that blocks are freed
-    void *get(int dev, size_t bytes) {
+    size_t held[64] = {};                                              // bytes cached per device
+    // bytes kept at most PER DEVICE (J2P_DEVCACHE_GB, default 8); beyond that blocks are freed
+    static size_t cap() {
+        static const size_t c = [] {
+            const char *e = getenv("J2P_DEVCACHE_GB");
+            const double gb = e && *e ? atof(e) : 8.0;
+            return (size_t)((gb < 0 ? 0 : gb) * (double)(1u << 30));
+        }();
+        return c;
+    }
+    // best fit: the smallest cached block of at least `bytes` that wastes at most a quarter of
+    // itself (a batch of JPEGs of many sizes re-uses blocks instead of piling up exact sizes)
+    void *get(int dev, size_t bytes, size_t *got) {
         std::lock_guard<std::mutex> l(mu);
-        auto it = blocks.find({dev, bytes});
-        if (it == blocks.end()) return nullptr;
+        auto it = blocks.lower_bound({dev, bytes});
+        if (it == blocks.end() || it->first.first != dev || it->first.second > bytes + bytes / 4 + 4096) return nullptr;
         void *p = it->second;
+        *got = it->first.second;
+        held[dev & 63] -= *got;
         blocks.erase(it);
-        held -= bytes;
         return p;
     }
     bool put(int dev, void *p, size_t bytes) {
         std::lock_guard<std::mutex> l(mu);
-        if (held + bytes > kCap) return false;
+        if (held[dev & 63] + bytes > cap()) return false;
         blocks.insert({{dev, bytes}, p});
-        held += bytes;
+        held[dev & 63] += bytes;
         return true;
+    }
+    // give every idle block of `dev` back to the driver (the current device must be `dev`)
+    void trim(int dev) {
+        std::lock_guard<std::mutex> l(mu);
+        for (auto it = blocks.lower_bound({dev, 0}); it != blocks.end() && it->first.first == dev;) {
+            cudaFree(it->second);
+            it = blocks.erase(it);
+        }
+        held[dev & 63] = 0;
     }
 };
 static DevCache g_dev_cache;
@@ -152,6 +170,7 @@ struct j2p_session {
     int16_t *data[3] = {};
     bool uploaded[3] = {};
     bool strip = false;       // row strip of a larger frame (multi-GPU tiling)
+    bool ipc_exported = false; // peers hold cudaIpc mappings of this session's plane buffers: never recycle them
     float pending_factor = 0.f;
     float t = 1.f;            // FISTA momentum state (compute.c:426)
     unsigned next_iter = 0;
@@ -171,12 +190,19 @@ struct j2p_session {
 template <typename T>
 static cudaError_t dev_alloc(j2p_session *s, T **p, size_t bytes) {
     bytes = bytes ? (bytes + 255) & ~(size_t)255 : 256;
-    void *q = g_dev_cache.get(s->device, bytes);
+    size_t got = bytes;
+    void *q = g_dev_cache.get(s->device, bytes, &got);
     if (!q) {
-        const cudaError_t e = cudaMalloc(&q, bytes);
+        got = bytes;
+        cudaError_t e = cudaMalloc(&q, bytes);
+        if (e == cudaErrorMemoryAllocation) {          // the cache may be sitting on the memory: release it, try once more
+            cudaGetLastError();
+            g_dev_cache.trim(s->device);
+            e = cudaMalloc(&q, bytes);
+        }
         if (e != cudaSuccess) return e;
     }
-    s->dev_blocks.push_back({q, bytes});
+    s->dev_blocks.push_back({q, got});
     *p = reinterpret_cast<T *>(q);
     return cudaSuccess;
 }
@@ -184,6 +210,7 @@ static cudaError_t dev_alloc(j2p_session *s, T **p, size_t bytes) {
 static std::once_flag g_cfg_once[64];
 static cudaError_t g_cfg_err[64];
 static int g_cfg_cc[64];
+static int g_cfg_slots[64];
 
 extern "C" const char *j2p_last_error(void) { return g_err; }
 
@@ -198,6 +225,26 @@ extern "C" int j2p_device_count(void) {
     return n;
 }
 
+// per-thread device binding of the drop-in entry (-1 = process default: J2P_DEVICE, else 0)
+static thread_local int g_thread_device = -1;
+
+extern "C" int j2p_set_thread_device(int device) {
+    if (device < 0) {
+        g_thread_device = -1;
+        return J2P_OK;
+    }
+    const int n = j2p_device_count();
+    if (device >= n) return fail(J2P_ERR_ARG, "device %d out of range (%d visible)", device, n);
+    g_thread_device = device;
+    return J2P_OK;
+}
+
+extern "C" int j2p_thread_device(void) {
+    if (g_thread_device >= 0) return g_thread_device;
+    const char *env = getenv("J2P_DEVICE");
+    return env && *env ? atoi(env) : 0;
+}
+
 extern "C" unsigned j2p_session_width(const j2p_session *s) { return s ? (unsigned)s->F.W : 0; }
 extern "C" unsigned j2p_session_height(const j2p_session *s) { return s ? (unsigned)s->F.Hg : 0; }
 extern "C" void *j2p_session_stream(j2p_session *s) { return s ? (void *)s->stream : nullptr; }
@@ -209,7 +256,7 @@ extern "C" void j2p_session_destroy(j2p_session *s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (auto &blk : s->dev_blocks)                   // the stream is idle: nothing uses the blocks any more
-        if (!g_dev_cache.put(s->device, blk.first, blk.second)) cudaFree(blk.first);
+        if (s->ipc_exported || !g_dev_cache.put(s->device, blk.first, blk.second)) cudaFree(blk.first);   // exported blocks go back to the driver, not to another session
     for (int i = 0; i < kEventRing; i++)
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     for (int k = 0; k < kStageSlots; k++) {          // the stream is idle: no DMA touches the ring any more
@@ -235,7 +282,7 @@ static int create_impl(j2p_session *s, int device, const j2p_frame_desc *d, unsi
         cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device);
         g_cfg_cc[device] = major * 10 + minor;
-        g_cfg_err[device] = e != cudaSuccess ? e : (major >= 10 ? configure_kernels() : cudaSuccess);
+        g_cfg_err[device] = e != cudaSuccess ? e : (major >= 10 ? configure_kernels(&g_cfg_slots[device]) : cudaSuccess);
     });
     if (g_cfg_cc[device] < 100)
         return fail(J2P_ERR_NODEVICE, "device %d is sm_%d; this library is built for sm_100a only", device, g_cfg_cc[device]);
@@ -281,6 +328,7 @@ static int create_impl(j2p_session *s, int device, const j2p_frame_desc *d, unsi
     const float tgv_alpha = d->weight / sqrtf((float)(4 / 2));          // compute.c:258
     F.a2 = (float)(((double)tgv_alpha * 1.) / (double)sqrtf((float)d->nchannel));   // compute.c:154
     F.use_tgv = d->weight != 0.f;                                       // compute.c:257
+    F.one = 1.0f;
 
     CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     for (int i = 0; i < kEventRing; i++) {
@@ -309,8 +357,9 @@ static int create_impl(j2p_session *s, int device, const j2p_frame_desc *d, unsi
         P.x = s->x[c]; P.xp = s->xp[c]; P.g = s->g[c]; P.gp = s->gp[c]; P.data = s->data[c];
     }
     F.grad_ctas = grad_cta_count(F.W, F.t1 - F.t0);
+    F.grad_slots = g_cfg_slots[device];
     CK(dev_alloc(s, &F.partials, sizeof(double) * 5 * (size_t)F.grad_ctas));
-    CK(dev_alloc(s, &F.norms, sizeof(float) * 8));
+    CK(dev_alloc(s, &F.norms, sizeof(float) * 16));     // [0..2] norms, [4..6] reciprocals, [8..10] strip sequence numbers
     CK(dev_alloc(s, &F.sums, sizeof(double) * 4));
     CK(dev_alloc(s, &F.logsums, sizeof(double) * 8));
     CK(cudaMemsetAsync(F.logsums, 0, sizeof(double) * 8, s->stream));
@@ -318,7 +367,7 @@ static int create_impl(j2p_session *s, int device, const j2p_frame_desc *d, unsi
     F.log_slot = 0;
     CK(dev_alloc(s, &F.counter, sizeof(unsigned)));
     CK(cudaMemsetAsync(F.counter, 0, sizeof(unsigned), s->stream));
-    CK(cudaMemsetAsync(F.norms, 0, sizeof(float) * 8, s->stream));
+    CK(cudaMemsetAsync(F.norms, 0, sizeof(float) * 16, s->stream));
     return J2P_OK;
 }
 
@@ -650,7 +699,13 @@ extern "C" int j2p_session_wait_iteration(j2p_session *s, unsigned iter) {
         CK(cudaEventSynchronize(s->ev[slot]));
     } else if (iter >= s->next_iter) {
         return fail(J2P_ERR_ARG, "iteration %u has not been queued", iter);
-    }   // else: its slot was recycled, so it finished long ago
+    } else {
+        // Its event slot has been recycled by a later iteration (more than kEventRing iterations were
+        // queued since).  Events mark where an iteration was QUEUED, so that alone says nothing about
+        // completion: wait for the iteration that took the slot — stream order makes the older one
+        // complete by then.
+        CK(cudaEventSynchronize(s->ev[slot]));
+    }
     return J2P_OK;
 }
 
@@ -773,17 +828,23 @@ struct j2p_comm {
     nccl_comm_t comm = nullptr;
     int nranks = 0, rank = 0, device = 0;
     double *gathered = nullptr;                                          // [nranks][3] fp64, device
-    // ---- peer-memory binding to one session (J2P_STRIP_P2P=1; kernels_strip.cu) ----
+    // ---- peer-memory binding to one session (the default; J2P_STRIP_P2P=0 keeps NCCL in the loop) ----
     j2p_session *bound = nullptr;
     int p2p_state = 0;                                                   // 0 = not tried, 1 = bound, -1 = unavailable (NCCL path)
     double *mail = nullptr;                                              // [2][nranks][4] doubles, written by every rank
-    unsigned *flags = nullptr;                                           // [2][nranks] mailbox flags, then from_up, from_down, ticket, err
+    // flag words of a rank: [0, 2*nranks) mailbox flags; then, at 2*nranks + k:
+    //   0 "my upper neighbour has delivered its rows", 1 "my lower neighbour has delivered",
+    //   2 ticket of the stand-alone halo kernel, 3 error word, 4/5 tickets of the border CTAs (top / bottom)
+    unsigned *flags = nullptr;
     std::vector<void *> opened;                                          // cudaIpcOpenMemHandle results to close again
-    StripPeers sp{};
+    double *peer_mail[8] = {};                                           // every rank's mailbox / flag block as mapped here (own: local)
+    unsigned *peer_flags[8] = {};
     float *up_buf[3][2] = {}, *down_buf[3][2] = {};                      // the neighbours' two plane buffers, mapped here
     unsigned *up_flags = nullptr, *down_flags = nullptr;                 // the neighbours' flag blocks, mapped here
     int up_t1 = 0, down_t0 = 0;                                          // the neighbours' owned-row bounds (their local indices)
-    unsigned seq_sums = 0, seq_halo = 0;
+    unsigned seq_sums = 0, seq_halo = 0;                                 // sums exchanges / halo deliveries so far (same on every rank)
+    int fused_halo = 0;                                                  // the projection kernels deliver the border rows themselves
+    unsigned border_ctas[2] = {0, 0};
 };
 
 #define NK(call)                                                                                      \
@@ -868,9 +929,9 @@ static int p2p_bind(j2p_comm *c, j2p_session *s, const NcclApi *api) {
     memset(&mine, 0, sizeof mine);
     mine.t0 = F.t0; mine.t1 = F.t1; mine.H = F.H; mine.W = F.W; mine.nc = F.nc;
     bool ok = cudaMalloc(&c->mail, sizeof(double) * 2 * nr * 4) == cudaSuccess &&
-              cudaMalloc(&c->flags, sizeof(unsigned) * (2 * nr + 4)) == cudaSuccess &&
+              cudaMalloc(&c->flags, sizeof(unsigned) * (2 * nr + 8)) == cudaSuccess &&
               cudaMemset(c->mail, 0, sizeof(double) * 2 * nr * 4) == cudaSuccess &&
-              cudaMemset(c->flags, 0, sizeof(unsigned) * (2 * nr + 4)) == cudaSuccess &&
+              cudaMemset(c->flags, 0, sizeof(unsigned) * (2 * nr + 8)) == cudaSuccess &&
               cudaIpcGetMemHandle(&mine.mail, c->mail) == cudaSuccess && cudaIpcGetMemHandle(&mine.flags, c->flags) == cudaSuccess;
     for (int k = 0; k < F.nc && ok; k++)
         ok = cudaIpcGetMemHandle(&mine.x[k], s->x[k]) == cudaSuccess && cudaIpcGetMemHandle(&mine.xp[k], s->xp[k]) == cudaSuccess;
@@ -894,12 +955,10 @@ static int p2p_bind(j2p_comm *c, j2p_session *s, const NcclApi *api) {
         return q;
     };
     if (ok) {
-        c->sp.nranks = nr;
-        c->sp.rank = c->rank;
         for (int p = 0; p < nr && ok; p++) {
-            if (p == c->rank) { c->sp.mail[p] = c->mail; c->sp.mail_flag[p] = c->flags; continue; }
-            c->sp.mail[p] = (double *)open(all[p].mail);
-            c->sp.mail_flag[p] = (unsigned *)open(all[p].flags);
+            if (p == c->rank) { c->peer_mail[p] = c->mail; c->peer_flags[p] = c->flags; continue; }
+            c->peer_mail[p] = (double *)open(all[p].mail);
+            c->peer_flags[p] = (unsigned *)open(all[p].flags);
             const bool up = p == c->rank - 1, down = p == c->rank + 1;
             if (!up && !down) continue;
             for (int k = 0; k < F.nc && ok; k++) {
@@ -907,8 +966,8 @@ static int p2p_bind(j2p_comm *c, j2p_session *s, const NcclApi *api) {
                 if (up) { c->up_buf[k][0] = b0; c->up_buf[k][1] = b1; }
                 else { c->down_buf[k][0] = b0; c->down_buf[k][1] = b1; }
             }
-            if (up) { c->up_flags = c->sp.mail_flag[p]; c->up_t1 = all[p].t1; }
-            else { c->down_flags = c->sp.mail_flag[p]; c->down_t0 = all[p].t0; }
+            if (up) { c->up_flags = c->peer_flags[p]; c->up_t1 = all[p].t1; }
+            else { c->down_flags = c->peer_flags[p]; c->down_t0 = all[p].t0; }
         }
     }
     // common verdict
@@ -922,11 +981,30 @@ static int p2p_bind(j2p_comm *c, j2p_session *s, const NcclApi *api) {
     cudaFree(d_all);
     for (int p = 0; p < nr; p++) ok = ok && oks[p] == 1;
     c->p2p_state = ok ? 1 : -1;
+    if (ok) {
+        s->ipc_exported = true;
+        // Can the projection kernels deliver the border rows themselves?  Needs every plane to span
+        // the frame width (no stepped-only columns at the strip borders) and to go through one of
+        // the two tiled projection kernels (1x1 or 2x2 sampling).  The same on every rank: it only
+        // depends on the frame description.
+        bool fused = true;
+        unsigned ctas = 0;
+        for (int k = 0; k < F.nc; k++) {
+            const PlaneDev &P = F.pl[k];
+            const bool tiled = (P.sw == 1 && P.sh == 1) || (P.sw == 2 && P.sh == 2);
+            fused = fused && tiled && P.cw * P.sw == F.W;
+            ctas += (unsigned)(((P.cw >> 3) + (P.sw == 1 ? 31 : 15)) / (P.sw == 1 ? 32 : 16));   // tiles per block row (kernels_project_tile*.cu)
+        }
+        const char *e = getenv("J2P_STRIP_FUSED_HALO");
+        if (e && *e == '0') fused = false;
+        c->fused_halo = fused ? 1 : 0;
+        c->border_ctas[0] = c->border_ctas[1] = ctas;
+    }
     return J2P_OK;
 }
 
 // the two border rows of the current iterate to both neighbours, over peer memory
-static int exchange_halos_p2p(j2p_session *s, j2p_comm *c) {
+static int exchange_halos_p2p(j2p_session *s, j2p_comm *c, int wait_for_arrival) {
     const FrameDev &F = s->F;
     const size_t W = (size_t)F.W;
     const int nr = c->nranks;
@@ -934,6 +1012,7 @@ static int exchange_halos_p2p(j2p_session *s, j2p_comm *c) {
     memset(&hp, 0, sizeof hp);
     hp.has_up = F.t0 > 0 && c->rank > 0;
     hp.has_down = F.t1 < F.H && c->rank + 1 < nr;
+    c->seq_halo++;                                                       // counted on every rank, also those without neighbours
     if (!hp.has_up && !hp.has_down) return J2P_OK;
     hp.nc = F.nc;
     hp.n4 = (unsigned)(2 * W / 4);
@@ -949,7 +1028,7 @@ static int exchange_halos_p2p(j2p_session *s, j2p_comm *c) {
     if (hp.has_down) hp.down_flag = c->down_flags + 2 * nr + 0;
     hp.from_up = c->flags + 2 * nr + 0;
     hp.from_down = c->flags + 2 * nr + 1;
-    CK(launch_halo_exchange(hp, ++c->seq_halo, c->flags + 2 * nr + 2, reinterpret_cast<int *>(c->flags + 2 * nr + 3), s->stream));
+    CK(launch_halo_exchange(hp, c->seq_halo, c->flags + 2 * nr + 2, reinterpret_cast<int *>(c->flags + 2 * nr + 3), wait_for_arrival, s->stream));
     s->launches++;
     return J2P_OK;
 }
@@ -976,9 +1055,50 @@ static int exchange_halos_nccl(j2p_session *s, j2p_comm *c, const NcclApi *api) 
     return J2P_OK;
 }
 
+// The in-kernel exchanges of one iteration (StripSync, kernels.cuh): sequence numbers and the
+// destinations of this iteration's border rows.  x_{k+1} is written over xp, so the rows go into
+// the neighbours' buffer with the same physical index (the x/xp roles alternate in lockstep on
+// every rank).
+static void fill_sync(j2p_session *s, j2p_comm *c) {
+    FrameDev &F = s->F;
+    StripSync &S = F.sync;
+    const size_t W = (size_t)F.W;
+    const int nr = c->nranks;
+    S.nranks = nr;
+    S.rank = c->rank;
+    S.seq = c->seq_sums + 1;
+    S.halo_seq = c->seq_halo;
+    S.fused_halo = c->fused_halo;
+    S.has_up = F.t0 > 0 && c->rank > 0;
+    S.has_down = F.t1 < F.H && c->rank + 1 < nr;
+    S.border_ctas[0] = c->border_ctas[0];
+    S.border_ctas[1] = c->border_ctas[1];
+    for (int p = 0; p < nr; p++) {
+        S.mail[p] = c->peer_mail[p];
+        S.mail_flag[p] = c->peer_flags[p];
+    }
+    S.my_mail = c->mail;
+    S.my_flag = c->flags;
+    for (int k = 0; k < F.nc; k++) {
+        const int b = F.pl[k].xp == s->x[k] ? 0 : 1;                      // physical buffer that receives x_{k+1}
+        S.up_dst[k] = S.has_up ? c->up_buf[k][b] + (size_t)c->up_t1 * W : nullptr;
+        S.down_dst[k] = S.has_down ? c->down_buf[k][b] + (size_t)(c->down_t0 - 2) * W : nullptr;
+    }
+    S.up_flag = S.has_up ? c->up_flags + 2 * nr + 1 : nullptr;
+    S.down_flag = S.has_down ? c->down_flags + 2 * nr + 0 : nullptr;
+    S.from_up = c->flags + 2 * nr + 0;
+    S.from_down = c->flags + 2 * nr + 1;
+    S.border_ticket = c->flags + 2 * nr + 4;
+    S.err = reinterpret_cast<int *>(c->flags + 2 * nr + 3);
+}
+
 // `n` iterations of this rank's strip; collective over the communicator (every rank calls it with
 // the same n).  The first call after (re)arming the session also fills the halo rows of x_0 and
 // x_{-1}.  Everything is queued on the session stream; use j2p_session_sync / download to wait.
+//
+// Peer-memory protocol (the default on one node): an iteration is exactly the two
+// solver kernels, the exchanges happen inside them.  J2P_STRIP_P2P=0, or peers whose memory cannot
+// be mapped, fall back to ncclAllGather + ncclSend/ncclRecv between the kernels.
 extern "C" int j2p_session_iterate_strip(j2p_session *s, j2p_comm *c, unsigned n) {
     if (!s || !c) return fail(J2P_ERR_ARG, "null argument");
     const NcclApi *api = nccl_api();
@@ -989,36 +1109,45 @@ extern "C" int j2p_session_iterate_strip(j2p_session *s, j2p_comm *c, unsigned n
         if (!s->uploaded[k]) return fail(J2P_ERR_ARG, "plane %d has not been uploaded", k);
     FrameDev &F = s->F;
     int rc;
-    // peer-memory protocol: opt-in (J2P_STRIP_P2P=1), bound to one session per communicator
-    static const bool want_p2p = [] { const char *e = getenv("J2P_STRIP_P2P"); return e && *e == '1'; }();
+    static const bool want_p2p = [] {
+        const char *e = getenv("J2P_STRIP_P2P"), *g = getenv("J2P_GRAD_SCALAR");
+        return !(e && *e == '0') && !(g && *g == '1');                   // the in-kernel exchanges live in the packed gradient kernel
+    }();
     if (want_p2p && c->p2p_state == 0 && (rc = p2p_bind(c, s, api)) != J2P_OK) return rc;
     const bool p2p = want_p2p && c->p2p_state == 1 && c->bound == s;
     if (s->next_iter == 0) {
-        if ((rc = p2p ? exchange_halos_p2p(s, c) : exchange_halos_nccl(s, c, api)) != J2P_OK) return rc;
+        if ((rc = p2p ? exchange_halos_p2p(s, c, 1) : exchange_halos_nccl(s, c, api)) != J2P_OK) return rc;
         if ((rc = j2p_session_copy_halo_to_prev(s)) != J2P_OK) return rc;
     }
     for (unsigned i = 0; i < n; i++) {
         const float tnext = (1 + sqrtf(1 + 4 * (s->t * s->t))) / 2;      // compute.c:431-432, :440
         const float factor = (s->t - 1) / tnext;
         s->t = tnext;
-        CK(launch_gradient(F, factor, s->stream));
+        int nproj = 0;
         if (p2p) {
-            CK(launch_sums_exchange(c->sp, F.sums, c->mail, c->flags, ++c->seq_sums, F.nc, F.norms,
-                                    reinterpret_cast<int *>(c->flags + 2 * c->nranks + 3), s->stream));
+            fill_sync(s, c);
+            CK(launch_gradient(F, factor, s->stream));                   // waits for the halo rows, posts the sums
+            CK(launch_project(F, factor, s->stream, &nproj));            // waits for the sums, delivers the border rows
+            F.sync.nranks = 0;                                           // the session's other entry points see a plain strip
+            c->seq_sums++;
+            s->launches += 1 + (unsigned)nproj;
         } else {
+            CK(launch_gradient(F, factor, s->stream));
             NK(api->AllGather(F.sums, c->gathered, 3, kNcclFloat64, c->comm, s->stream));
             CK(launch_fold_sums(c->gathered, c->nranks, F.nc, F.norms, s->stream));
+            CK(launch_project(F, factor, s->stream, &nproj));
+            s->launches += 2 + (unsigned)nproj;                          // gradient, fold, projection launches
         }
-        int nproj = 0;
-        CK(launch_project(F, factor, s->stream, &nproj));
-        s->launches += 2 + (unsigned)nproj;                              // gradient, sums exchange / fold, projection launches
         for (int k = 0; k < F.nc; k++) {                                 // compute.c:438
             float *tmp = F.pl[k].x;
             F.pl[k].x = F.pl[k].xp;
             F.pl[k].xp = tmp;
         }
         s->next_iter++;
-        if ((rc = p2p ? exchange_halos_p2p(s, c) : exchange_halos_nccl(s, c, api)) != J2P_OK) return rc;
+        if (p2p) {
+            if (c->fused_halo) c->seq_halo++;                            // delivered by the projection kernels
+            else if ((rc = exchange_halos_p2p(s, c, 0)) != J2P_OK) return rc;   // stand-alone copy, no wait: the next gradient waits
+        } else if ((rc = exchange_halos_nccl(s, c, api)) != J2P_OK) return rc;
     }
     return J2P_OK;
 }

@@ -4,6 +4,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
 
 
 def test_shared_reciprocal_division_is_correctly_rounded(tmp_path):
@@ -25,3 +26,42 @@ def test_row_guard_property(tmp_path):
     r = subprocess.run([str(exe), '5000000'], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert ' 0 below 2^-60' in r.stdout
+
+
+def test_packed_products_are_not_contracted(tmp_path):
+    """ptxas 12.9 fuses mul.rn.f32x2 + add/sub.rn.f32x2 into one FFMA2 (a single rounding where
+    the reference has two) although the operations carry an explicit .rn and the build passes
+    --fmad=false; NVIDIA's own __fadd2_rn(__fmul2_rn(x, y), z) is affected too.  The packed
+    gradient kernel therefore routes every sum with a product through addm2() (numerics.cuh).
+    This test is the tripwire: for every instantiation of k_gradient_packed the SASS must contain
+    exactly as many FFMA2 / FMUL2 / FADD2 as the PTX has fma / mul / add+sub .rn.f32x2 — a
+    contraction would turn one FMUL2 and one FADD2 into an extra FFMA2."""
+    import collections
+    import re
+    import shutil
+    import subprocess
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    cuobjdump = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not (os.path.exists(nvcc) and os.path.exists(cuobjdump)):
+        import pytest
+        pytest.skip('CUDA toolkit not installed')
+    src = os.path.join(ROOT, 'jpeg2png_b200', 'csrc', 'kernels_gradient_packed.cu')
+    flags = ['-O3', '-std=c++17', '-fmad=false', '-prec-div=true', '-prec-sqrt=true', '-ftz=false']
+    ptx, cubin = str(tmp_path / 'k.ptx'), str(tmp_path / 'k.cubin')
+    subprocess.run([nvcc, '-gencode', 'arch=compute_100a,code=compute_100a', *flags, '-ptx', '-o', ptx, src], check=True, capture_output=True)
+    subprocess.run([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', *flags, '-cubin', '-o', cubin, src], check=True, capture_output=True)
+    want = {}
+    for entry in re.split(r'\n\.visible \.entry ', open(ptx).read())[1:]:
+        c = collections.Counter(re.findall(r'\b(fma|mul|add|sub)\.rn\.f32x2\b', entry))
+        want[entry.split('(')[0].strip()] = (c['fma'], c['mul'], c['add'] + c['sub'])
+    sass = subprocess.run([cuobjdump, '-sass', cubin], check=True, capture_output=True, text=True).stdout
+    seen = 0
+    for fun in re.split(r'\n\s+Function : ', sass)[1:]:
+        name = fun.split('\n')[0].strip()
+        if name not in want:
+            continue
+        c = collections.Counter(re.findall(r'\b(FFMA2|FMUL2|FADD2)\b', fun))
+        assert (c['FFMA2'], c['FMUL2'], c['FADD2']) == want[name], f'{name}: SASS {dict(c)} vs PTX fma/mul/add+sub {want[name]}'
+        assert want[name][0] > 30, 'the kernel no longer uses packed fp32?'
+        seen += 1
+    assert seen >= 12
