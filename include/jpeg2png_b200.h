@@ -62,7 +62,9 @@ struct progressbar;
  *     freed, compute.c:304-305, :458) otherwise;
  *   - overwrites coefs[c].w/h with the frame size W,H (compute.c:460-461);
  *   - re-entrant: may be called concurrently from several host threads (jpeg2png.c:147, :330);
- *     each call uses its own CUDA stream and no mutable global state;
+ *     each call has its own CUDA stream and device buffers.  What the calls share is internally
+ *     locked and holds no solver state: a cache of idle device blocks, pinned staging buffers and
+ *     the host copy threads;
  *   - errors: message on stderr prefixed "jpeg2png: " and exit(EXIT_FAILURE) (utils.c:11-28).
  *
  * The callbacks are resolved at link time exactly like in the reference: the host program
@@ -142,24 +144,30 @@ int j2p_session_halo(j2p_session *s, unsigned channel, int side, void **send, vo
                      size_t *count);
 int j2p_session_copy_halo_to_prev(j2p_session *s);
 
-/* Native strip loop: the same iteration with both exchanges queued on the session stream through
- * NCCL (resolved at run time with dlopen("libnccl.so.2"); no link-time dependency), so the host
- * never waits inside the loop.  One process per GPU: rank 0 obtains an id with
- * j2p_comm_unique_id(), hands its 128 bytes to the other ranks by any means (the Python driver
- * broadcasts it with torch.distributed), every rank calls j2p_comm_create().  Ranks are the strips
- * in top-to-bottom order.  j2p_session_iterate_strip() is collective; its first call after
- * (re)arming a session also exchanges the halos of the initial iterate. */
+/* Native strip loop.  One process per GPU: rank 0 obtains an id with j2p_comm_unique_id(), hands
+ * its 128 bytes to the other ranks by any means (the Python driver broadcasts it with
+ * torch.distributed), every rank calls j2p_comm_create().  Ranks are the strips in top-to-bottom
+ * order.  j2p_session_iterate_strip() is collective; its first call after (re)arming a session also
+ * exchanges the halos of the initial iterate; the host never waits inside the loop.
+ *
+ * On one node (up to 8 ranks) the first call maps the peers' memory (cudaIpc over NVLink) and from
+ * then on an iteration is exactly the two solver kernels: the gradient kernel's last CTA stores
+ * this rank's sums of g^2 into every rank's mailbox, the projection kernels wait for all of them,
+ * fold them in rank order and store the strip's border rows straight into the neighbours' halo
+ * rows, the next gradient kernel's border bands wait for those (sequence-numbered flags,
+ * st.release.sys / ld.acquire.sys).  When peer memory cannot be mapped, or with J2P_STRIP_P2P=0, the
+ * exchanges are ncclAllGather + ncclSend/ncclRecv queued between the kernels.  NCCL is resolved at
+ * run time with dlopen("libnccl.so.2"): no link-time dependency.  Same results either way.
+ * Destroy the communicator before the session it was used with. */
 typedef struct j2p_comm j2p_comm;
 #define J2P_COMM_ID_BYTES 128
 int j2p_comm_unique_id(void *out, size_t bytes);
 int j2p_comm_create(j2p_comm **out, int device, int nranks, int rank, const void *id, size_t bytes);
 void j2p_comm_destroy(j2p_comm *c);
 int j2p_session_iterate_strip(j2p_session *s, j2p_comm *c, unsigned n);
-/* 0, or an error if a peer-memory exchange timed out on the device.  Only the opt-in peer-memory
- * protocol can fail this way (environment J2P_STRIP_P2P=1: the ranks store the sums and the border
- * rows straight into each other's memory over NVLink, cudaIpc mappings, instead of calling NCCL
- * inside the loop; same results).  Synchronises the device.  Destroy the communicator before the
- * session it was used with. */
+/* 0, or an error if an in-kernel wait of the peer-memory protocol timed out on the device (a peer
+ * died; results are invalid; every wait gives up after about two seconds of GPU clock instead of
+ * hanging the device).  Synchronises the device. */
 int j2p_comm_status(j2p_comm *c);
 /* 1 if j2p_session_iterate_strip exchanges through peer memory, 0 if through NCCL. */
 int j2p_comm_protocol(const j2p_comm *c);
@@ -196,6 +204,15 @@ int j2p_session_wait_iteration(j2p_session *s, unsigned iter);
 
 /* HBM -> host: the current iterate of `channel`, H x W floats raster. */
 int j2p_session_download(j2p_session *s, unsigned channel, float *out);
+
+/* HBM -> host, joint (3-plane) whole-frame sessions: the image as the reference hands it to libpng,
+ * computed on the device — luma += 128 (jpeg2png.c:156-159), YCbCr -> RGB in double, clamp,
+ * scale by (1 << bits)/256, truncate (png.c:39-47), 8-bit or 16-bit big-endian samples
+ * (png.c:51-62) — laid out as PNG scanlines: h rows of 1 + w*3*bits/8 bytes, every row starting
+ * with filter type 0.  w x h is the visible image (jpeg->w, jpeg->h), at most the frame size.
+ * 3 or 6 bytes per pixel cross PCIe instead of 12. */
+int j2p_session_download_scanlines(j2p_session *s, unsigned w, unsigned h, unsigned bits,
+                                   unsigned char *out);
 
 /* Objective terms of the most recent iteration, as logged by the reference (compute.c:271-272):
  * out[0]=objective, out[1]=prob_dist, out[2]=tv, out[3]=tv2.  Only tracked when logging was

@@ -173,6 +173,8 @@ def declare_product(lib: C.CDLL) -> C.CDLL:
     lib.j2p_session_wait_iteration.argtypes = [vp, C.c_uint]
     lib.j2p_session_download.restype = C.c_int
     lib.j2p_session_download.argtypes = [vp, C.c_uint, vp]
+    lib.j2p_session_download_scanlines.restype = C.c_int
+    lib.j2p_session_download_scanlines.argtypes = [vp, C.c_uint, C.c_uint, C.c_uint, vp]
     lib.j2p_session_set_logging.restype = C.c_int
     lib.j2p_session_set_logging.argtypes = [vp, C.c_int]
     lib.j2p_session_objective.restype = C.c_int
@@ -199,7 +201,7 @@ HEADER_SYMBOLS = [
     'j2p_session_width', 'j2p_session_height', 'j2p_session_upload', 'j2p_session_reset',
     'j2p_session_iterate', 'j2p_session_profile', 'j2p_session_wait_iteration', 'j2p_session_download', 'j2p_session_set_logging',
     'j2p_session_objective', 'j2p_session_sync', 'j2p_session_stream', 'j2p_session_plane_ptr',
-    'j2p_session_launches', 'j2p_version', 'j2p_host_prefault', 'j2p_set_thread_device', 'j2p_thread_device',
+    'j2p_session_launches', 'j2p_version', 'j2p_host_prefault', 'j2p_set_thread_device', 'j2p_thread_device', 'j2p_session_download_scanlines',
 ]
 
 _product = None

@@ -112,8 +112,11 @@ struct job {
         bool all_together, quiet;
 };
 
+/* out: the float planes (separate mode), or — joint mode, scanlines != NULL — nothing: the image comes
+ * back as PNG scanlines, converted on the device (j2p_session_download_scanlines) */
 static void solve(const struct j2p_jpeg *jpeg, const unsigned *chan, unsigned nchan, int device, const struct job *job, unsigned iterations,
-                  float weight, struct progressbar *pb, const char *infile, unsigned log_channel, float **out, unsigned *out_w, unsigned *out_h) {
+                  float weight, struct progressbar *pb, const char *infile, unsigned log_channel, float **out, unsigned *out_w, unsigned *out_h,
+                  uint8_t **scanlines) {
         struct j2p_frame_desc d;
         memset(&d, 0, sizeof d);
         d.nchannel = nchan;
@@ -144,12 +147,40 @@ static void solve(const struct j2p_jpeg *jpeg, const unsigned *chan, unsigned nc
         if (pb) for (; reported < iterations; reported++) { j2p_session_wait_iteration(s, reported); pb_add(pb, 1); }
         *out_w = j2p_session_width(s);
         *out_h = j2p_session_height(s);
+        if (scanlines) {
+                *scanlines = malloc((size_t)jpeg->h * ((size_t)jpeg->w * 3 * (job->png_bits / 8) + 1));
+                if (!*scanlines) die("allocation error");
+                if (j2p_session_download_scanlines(s, jpeg->w, jpeg->h, job->png_bits, *scanlines) != J2P_OK) die("%s", j2p_last_error());
+                j2p_session_destroy(s);
+                return;
+        }
         for (unsigned k = 0; k < nchan; k++) {
                 out[k] = aligned_alloc(16, (((size_t)*out_w * *out_h * sizeof(float)) + 15) & ~(size_t)15);
                 if (!out[k]) die("allocation error");
                 if (j2p_session_download(s, k, out[k]) != J2P_OK) die("%s", j2p_last_error());
         }
         j2p_session_destroy(s);
+}
+
+/* CPUs this process may really use: the affinity mask capped by the cgroup quota.  The GPU boxes
+ * show 128 hardware threads and grant 16 CPUs; an OpenMP team as wide as the machine then spends
+ * its quota on context switches (round 1: threads 90..126 in the batch trace). */
+static int usable_cpus(void) {
+        int n = 1;
+#ifdef _OPENMP
+        n = omp_get_num_procs();
+#endif
+        FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r");
+        if (f) {
+                char quota[32];
+                long period = 0;
+                if (fscanf(f, "%31s %ld", quota, &period) == 2 && period > 0 && strcmp(quota, "max") != 0) {
+                        const long q = (atol(quota) + period - 1) / period;
+                        if (q > 0 && q < n) n = (int)q;
+                }
+                fclose(f);
+        }
+        return n > 0 ? n : 1;
 }
 
 static double now_ms(void) {
@@ -177,22 +208,31 @@ static void decode_file(const char *infile, const char *outfile, const struct jo
 
         const double t_read = trace ? now_ms() : 0;
         float *planes[3] = {NULL, NULL, NULL};
+        uint8_t *scanlines = NULL;
         unsigned pw[3], ph[3];
         if (job->all_together) {                                                 /* jpeg2png.c:142-144 */
+                /* the +128 of jpeg2png.c:156-159 and the colour conversion of png.c:39-62 run on the device */
                 const unsigned chan[3] = {0, 1, 2};
                 unsigned w, h;
-                solve(&jpeg, chan, 3, device, job, job->iterations[0], job->weights[0], pb, infile, 3, planes, &w, &h);
-                for (int i = 0; i < 3; i++) { pw[i] = w; ph[i] = h; }
+                solve(&jpeg, chan, 3, device, job, job->iterations[0], job->weights[0], pb, infile, 3, planes, &w, &h, &scanlines);
         } else {                                                                 /* jpeg2png.c:146-152: each plane computes its own frame size */
-                for (unsigned i = 0; i < 3; i++) solve(&jpeg, &i, 1, device, job, job->iterations[i], job->weights[i], pb, infile, i, &planes[i], &pw[i], &ph[i]);
+                /* three independent solves, concurrently like the reference's OpenMP loop, on up to three
+                 * devices (inside the file-parallel loop nested parallelism is off and they run in turn) */
+                const int ndev = j2p_device_count();
+#pragma omp parallel for schedule(static, 1) num_threads(3)
+                for (unsigned i = 0; i < 3; i++)
+                        solve(&jpeg, &i, 1, (device + (int)i) % (ndev > 0 ? ndev : 1), job, job->iterations[i], job->weights[i], pb, infile, i, &planes[i], &pw[i], &ph[i], NULL);
+                for (size_t i = 0; i < (size_t)pw[0] * ph[0]; i++) planes[0][i] += 128.f;   /* jpeg2png.c:156-159 */
         }
-        for (size_t i = 0; i < (size_t)pw[0] * ph[0]; i++) planes[0][i] += 128.f;   /* jpeg2png.c:156-159 */
         const double t_solve = trace ? now_ms() : 0;
 
         FILE *out = fopen(outfile, "wb");
         if (!out) { if (main_pb) { pb_clear(); main_pb = NULL; } fprintf(stderr, "jpeg2png: could not open output file `%s`: ", outfile); perror(NULL); exit(EXIT_FAILURE); }
-        if (j2p_write_png(out, jpeg.w, jpeg.h, job->png_bits, planes[0], pw[0], planes[1], pw[1], planes[2], pw[2]) != 0) die("could not write PNG file `%s`", outfile);
+        const int wrc = scanlines ? j2p_write_png_scanlines(out, jpeg.w, jpeg.h, job->png_bits, scanlines)
+                                  : j2p_write_png(out, jpeg.w, jpeg.h, job->png_bits, planes[0], pw[0], planes[1], pw[1], planes[2], pw[2]);
+        if (wrc != 0) die("could not write PNG file `%s`", outfile);
         fclose(out);
+        free(scanlines);
         for (int i = 0; i < 3; i++) { free(planes[i]); free(jpeg.coefs[i].data); }
         if (trace)
                 fprintf(stderr, "j2p trace: %s: read+parse %.1f ms, solve (upload..download) %.1f ms, colour+PNG %.1f ms (thread %d, started at %.1f)\n", infile,
@@ -278,6 +318,10 @@ int main(int argc, char **argv) {
                 if (sscanf(arg_t, "%u", &threads) != 1 || threads == 0) die("invalid number of threads");
 #ifdef _OPENMP
                 omp_set_num_threads((int)threads);
+#endif
+        } else {
+#ifdef _OPENMP
+                if (!getenv("OMP_NUM_THREADS")) omp_set_num_threads(usable_cpus());
 #endif
         }
         if (arg_c) {

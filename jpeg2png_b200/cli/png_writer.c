@@ -59,7 +59,15 @@ static int put_chunk(FILE *f, const char *type, const uint8_t *data, size_t len)
 #define J2P_PIECE ((size_t)1 << 20)
 #define J2P_FAIL() do { _Pragma("omp atomic write") failed = 1; } while (0)
 
+/* Compression effort: the reference leaves libpng at zlib level 6.  What must match is the pixels,
+ * not the file bytes, and on a GPU the deflate of a multi-megapixel image costs several times the
+ * solve it follows (profiles/r01_cli_batch.txt: 170-290 ms per 1080p file against 30 ms).  Images
+ * of a megapixel or more are therefore deflated at level 1 (about 4x faster, files ~10-15 % larger);
+ * small images keep level 6. */
+static int deflate_level(size_t raw_bytes) { return raw_bytes >= (size_t)3 << 20 ? 1 : 6; }
+
 static uint8_t *deflate_pieces(const uint8_t *raw, size_t len, size_t *zlen) {
+        const int level = deflate_level(len);
         const size_t np = (len + J2P_PIECE - 1) / J2P_PIECE;
         uint8_t **buf = calloc(np, sizeof *buf);
         size_t *blen = calloc(np, sizeof *blen);
@@ -71,7 +79,7 @@ static uint8_t *deflate_pieces(const uint8_t *raw, size_t len, size_t *zlen) {
                 const size_t off = (size_t)i * J2P_PIECE, n = len - off < J2P_PIECE ? len - off : J2P_PIECE;
                 z_stream zs;
                 memset(&zs, 0, sizeof zs);
-                if (deflateInit2(&zs, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { J2P_FAIL(); continue; }
+                if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { J2P_FAIL(); continue; }
                 const size_t cap = deflateBound(&zs, (uLong)n) + 64;
                 buf[i] = malloc(cap);
                 if (buf[i]) {
@@ -114,14 +122,10 @@ static uint8_t *deflate_pieces(const uint8_t *raw, size_t len, size_t *zlen) {
         return z;
 }
 
-int j2p_write_png(FILE *out, unsigned w, unsigned h, unsigned bits, const float *y, unsigned ys, const float *cb, unsigned cbs,
-                  const float *cr, unsigned crs) {
+/* `raw`: h scanlines of 1 + w*3*bits/8 bytes, each starting with its filter-type byte */
+int j2p_write_png_scanlines(FILE *out, unsigned w, unsigned h, unsigned bits, const uint8_t *raw) {
         if (bits != 8 && bits != 16) return -1;
-        const size_t row = (size_t)w * 3 * (bits / 8), stride = row + 1;      /* +1: filter-type byte */
-        uint8_t *raw = malloc(stride * h);
-        if (!raw) return -1;
-        for (unsigned i = 0; i < h; i++) raw[(size_t)i * stride] = 0;          /* filter 0 (None) */
-        j2p_ycc_to_rgb(w, h, bits, y, ys, cb, cbs, cr, crs, raw + 1, stride);
+        const size_t stride = (size_t)w * 3 * (bits / 8) + 1;
         size_t zlen = 0;
         uint8_t *z = NULL;
         if (stride * h > 2 * J2P_PIECE) {
@@ -129,7 +133,7 @@ int j2p_write_png(FILE *out, unsigned w, unsigned h, unsigned bits, const float 
         } else {
                 uLongf zl = compressBound((uLong)(stride * h));
                 z = malloc(zl);
-                if (z && compress2(z, &zl, raw, (uLong)(stride * h), 6) == Z_OK) zlen = zl;
+                if (z && compress2(z, &zl, raw, (uLong)(stride * h), deflate_level(stride * h)) == Z_OK) zlen = zl;
                 else { free(z); z = NULL; }
         }
         int rc = -1;
@@ -142,6 +146,18 @@ int j2p_write_png(FILE *out, unsigned w, unsigned h, unsigned bits, const float 
                         rc = 0;
         }
         free(z);
+        return rc;
+}
+
+int j2p_write_png(FILE *out, unsigned w, unsigned h, unsigned bits, const float *y, unsigned ys, const float *cb, unsigned cbs,
+                  const float *cr, unsigned crs) {
+        if (bits != 8 && bits != 16) return -1;
+        const size_t row = (size_t)w * 3 * (bits / 8), stride = row + 1;      /* +1: filter-type byte */
+        uint8_t *raw = malloc(stride * h);
+        if (!raw) return -1;
+        for (unsigned i = 0; i < h; i++) raw[(size_t)i * stride] = 0;          /* filter 0 (None) */
+        j2p_ycc_to_rgb(w, h, bits, y, ys, cb, cbs, cr, crs, raw + 1, stride);
+        const int rc = j2p_write_png_scanlines(out, w, h, bits, raw);
         free(raw);
         return rc;
 }

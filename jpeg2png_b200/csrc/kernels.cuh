@@ -54,6 +54,10 @@ struct FrameDev {
     int y0g;              // frame row of local row 0
     int t0, t1;           // local rows [t0, t1) this session owns (targets); the rest is halo
     PlaneDev pl[3];
+    float *slab;          // the allocation that holds x, xp, g, gp of every plane
+    const void *host_maps;// host pointer to the session's TileMaps (tma_maps.h), or null: no TMA path for this session
+    int buf_sel;          // 0: pl[c].x is the session's first iterate buffer, 1: the second (which tensor map is x_k)
+    unsigned plane_stride;// elements between consecutive planes of one array: pl[c].x == pl[0].x + c * plane_stride, same for xp, g, gp
     float q[3][64];       // quantisation tables as float
     float qq[3][64];      // q*q (fp32 product, compute.c:49)
     float rqq[3][64];     // RN(1/(q*q)), the shared reciprocal of the residual division

@@ -80,16 +80,18 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient_packed(co
     }
     A.ok1 = A.ok2 = true;
 
-    // column part of the gp addressing
+    // which pixels have a DCT-distance term (compute.c:58-62 footprint, pweight != 0).  GPM 1, 2: every
+    // in-frame pixel of a plane with pweight != 0 (values of out-of-frame lanes are never stored), so
+    // the mask is warp-uniform; generic: per pixel.
     int gpx[NC][2];
 #pragma unroll
     for (int c = 0; c < NC; c++) {
         float m[2];
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-            const int cx = GPM == 1 ? px0 + k : (px0 + k) / F.pl[c].sw;
-            const bool has = F.pl[c].use_prob && pair_in && cx < F.pl[c].cw;
-            gpx[c][k] = has ? cx : 0;
+            const int cx = (px0 + k) / F.pl[c].sw;
+            const bool has = F.pl[c].use_prob && (GPM != 0 || (pair_in && cx < F.pl[c].cw));
+            gpx[c][k] = has && GPM == 0 ? cx : 0;
             m[k] = has ? 1.f : 0.f;
         }
         gmask[c] = pk(m[0], m[1]);
@@ -97,14 +99,42 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient_packed(co
 
     // Rows/columns outside the frame are never consumed (their sources are dead), so the loads are
     // made unconditional by clamping the address into the frame: no branches.
+    //
+    // Addressing (GPM != 0).  The session keeps x[0..2], xp[0..2], g[0..2], gp[0..2] in one slab with
+    // the same element stride PS between the planes of an array (session.cu).  The kernel holds ONE
+    // 64-bit lane pointer per array (array base + the lane's column, made opaque so that it stays in
+    // registers) and forms an address as
+    //     lane pointer + 4 * (row * W + c * PS)        row * W + c * PS is warp-uniform, 32 bits
+    // With one pointer per buffer in the parameter block the compiler re-read the pointers with LDC every
+    // row; those LDCs shared a scoreboard with the loads already in flight, each address waited for the
+    // previous loads to land, and the one-row prefetch was lost (44 % issue-active at 17 % occupancy,
+    // long_scoreboard the top stall; profiles/r02_notes.md).
     const int pxc = pair_in ? px0 : 0;
+    const unsigned PS = F.plane_stride;
+    unsigned long long lp_x = 0, lp_xp = 0, lp_g = 0, lp_gp = 0, lp_gpc = 0;
+    if (GPM != 0) {
+        asm volatile("mad.wide.s32 %0, %1, 4, %2;" : "=l"(lp_x) : "r"(pxc), "l"(F.pl[0].x));
+        asm volatile("mad.wide.s32 %0, %1, 4, %2;" : "=l"(lp_xp) : "r"(pxc), "l"(F.pl[0].xp));
+        asm volatile("mad.wide.s32 %0, %1, 4, %2;" : "=l"(lp_g) : "r"(pxc), "l"(F.pl[0].g));
+        asm volatile("mad.wide.s32 %0, %1, 4, %2;" : "=l"(lp_gp) : "r"(pxc), "l"(F.pl[0].gp));
+        if (GPM == 2) asm volatile("mad.wide.s32 %0, %1, 4, %2;" : "=l"(lp_gpc) : "r"(pxc >> 1), "l"(F.pl[0].gp));   // 2x2 planes: one sample per pixel pair
+    }
+    auto at = [](unsigned long long base, unsigned elem) {          // base + 4 * elem
+        unsigned long long a;
+        asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(a) : "r"(elem), "l"(base));
+        return a;
+    };
     auto issue_row_loads = [&](int row) {
-        const int rc = min(max(row, 0), H - 1);
-        const unsigned gi = (unsigned)rc * (unsigned)W + (unsigned)pxc;   // frames are far below 2^32 pixels (checked at session creation)
+        const unsigned ro = (unsigned)min(max(row, 0), H - 1) * (unsigned)W;   // slabs are below 2^32 elements (checked at session creation)
 #pragma unroll
         for (int c = 0; c < NC; c++) {
-            ldx[c] = *reinterpret_cast<const float2 *>(F.pl[c].x + gi);
-            ldp[c] = *reinterpret_cast<const float2 *>(F.pl[c].xp + gi);
+            if (GPM != 0) {
+                ldx[c] = *reinterpret_cast<const float2 *>(at(lp_x, ro + c * PS));
+                ldp[c] = *reinterpret_cast<const float2 *>(at(lp_xp, ro + c * PS));
+            } else {
+                ldx[c] = *reinterpret_cast<const float2 *>(F.pl[c].x + (ro + (unsigned)pxc));
+                ldp[c] = *reinterpret_cast<const float2 *>(F.pl[c].xp + (ro + (unsigned)pxc));
+            }
         }
     };
     // coefficient-grid row of the next target row, tracked incrementally (no per-step division)
@@ -112,18 +142,31 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient_packed(co
 #pragma unroll
     for (int c = 0; c < NC; c++) {
         const int r0 = yb - F.t0;                   // coefficient rows are stored from the first owned row
-        gcy[c] = GPM == 1 ? r0 : r0 / F.pl[c].sh;
-        grem[c] = GPM == 1 ? 0 : r0 - gcy[c] * F.pl[c].sh;
+        gcy[c] = GPM == 0 ? r0 / F.pl[c].sh : 0;
+        grem[c] = GPM == 0 ? r0 - gcy[c] * F.pl[c].sh : 0;
     }
     unsigned gp_rows_ok = 0;            // bit c: the prefetched gp row exists
     auto issue_gp_loads = [&](int row) {   // for target rows yb, yb+1, ... in order; raw loads only
-        if (GPM == 1) {                     // gp has the frame's geometry and every target row has its gp row
-            const unsigned gi = (unsigned)(row - F.t0) * (unsigned)W + (unsigned)pxc;
+        const unsigned r = (unsigned)(row - F.t0);                  // coefficient rows are stored from the first owned row
+        if (GPM == 1) {                     // every gp plane has the frame's geometry and every target row has its gp row
 #pragma unroll
             for (int c = 0; c < NC; c++) {
-                const float2 v = *reinterpret_cast<const float2 *>(F.pl[c].gp + gi);
+                const float2 v = *reinterpret_cast<const float2 *>(at(lp_gp, r * (unsigned)W + c * PS));
                 pgp[c] = pk(v.x, v.y);
             }
+            return;
+        }
+        if (GPM == 2) {                     // 4:2:0 with aligned grids: plane 0 full resolution, planes 1, 2 at half resolution
+            const bool ok0 = r < (unsigned)F.pl[0].ch;              // 1080p: luma rows 1080..1087 have no term (warp-uniform)
+            const float2 v = *reinterpret_cast<const float2 *>(at(lp_gp, (ok0 ? r : 0u) * (unsigned)W));
+            pgp[0] = pk(v.x, v.y);
+            const unsigned rc_ = min(r >> 1, (unsigned)F.pl[1].ch - 1u) * (unsigned)(W >> 1);
+#pragma unroll
+            for (int c = 1; c < NC; c++) {
+                const float u = *reinterpret_cast<const float *>(at(lp_gpc, rc_ + c * PS));
+                pgp[c] = pk(u, u);
+            }
+            gp_rows_ok = (ok0 ? 1u : 0u) | ((r >> 1) < (unsigned)F.pl[1].ch ? 6u : 0u);
             return;
         }
         gp_rows_ok = 0;
@@ -307,10 +350,11 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient_packed(co
                 }
             }
             if (is_target) {
-                const unsigned gi = (unsigned)(s - 1) * (unsigned)W + (unsigned)px0;
+                const unsigned ro = (unsigned)(s - 1) * (unsigned)W;           // targets are inside the frame: pxc == px0
 #pragma unroll
                 for (int c = 0; c < NC; c++) {
-                    *reinterpret_cast<float2 *>(F.pl[c].g + gi) = make_float2(lo(o[c]), hi(o[c]));
+                    float2 *dst = GPM != 0 ? reinterpret_cast<float2 *>(at(lp_g, ro + c * PS)) : reinterpret_cast<float2 *>(F.pl[c].g + (ro + (unsigned)px0));
+                    *dst = make_float2(lo(o[c]), hi(o[c]));
                     const f2 sq = mul2(o[c], o[c]);
                     acc[c] = __dadd_rn(acc[c], (double)lo(sq));       // compute.c:203
                     acc[c] = __dadd_rn(acc[c], (double)hi(sq));
@@ -420,11 +464,18 @@ cudaError_t launch_gradient_packed(const FrameDev &F, float factor, cudaStream_t
     int cx, bands, rows;
     grad_geometry(F.W, F.t1 - F.t0, F.grad_slots, &cx, &bands, &rows);
     const dim3 grid(cx, bands);
+    const int owned = F.t1 - F.t0;
     bool full = true;      // every plane at full resolution over the whole (local) frame: gp has the frame's geometry
-    for (int c = 0; c < F.nc; c++) full = full && F.pl[c].sw == 1 && F.pl[c].sh == 1 && F.pl[c].cw == F.W && F.pl[c].ch >= F.t1 - F.t0;
+    for (int c = 0; c < F.nc; c++) full = full && F.pl[c].sw == 1 && F.pl[c].sh == 1 && F.pl[c].cw == F.W && F.pl[c].ch >= owned;
+    // 4:2:0 with aligned grids: luma full width (its last rows may be missing: 1080p), both chroma planes exactly half
+    bool c420 = F.nc == 3 && F.pl[0].sw == 1 && F.pl[0].sh == 1 && F.pl[0].cw == F.W;
+    for (int c = 1; c < 3 && c420; c++) c420 = F.pl[c].sw == 2 && F.pl[c].sh == 2 && 2 * F.pl[c].cw == F.W && F.pl[c].ch == F.pl[1].ch;
     if (full) {
         if (F.use_tgv) launch_packed_nc<true, 1>(F, factor, grid, rows, s);
         else launch_packed_nc<false, 1>(F, factor, grid, rows, s);
+    } else if (c420) {
+        if (F.use_tgv) k_gradient_packed<3, true, 2><<<grid, GM_NT, 0, s>>>(F, factor, rows);
+        else k_gradient_packed<3, false, 2><<<grid, GM_NT, 0, s>>>(F, factor, rows);
     } else {
         if (F.use_tgv) launch_packed_nc<true, 0>(F, factor, grid, rows, s);
         else launch_packed_nc<false, 0>(F, factor, grid, rows, s);

@@ -7,11 +7,15 @@
 #include "numerics.cuh"
 #include "project_common.cuh"
 #include "strip_sync.cuh"
+#include "tma_maps.h"
 
 
 namespace j2p {
 
-cudaError_t launch_project_tile(const FrameDev &F, int c, int count, float factor, cudaStream_t s, int *nlaunch);
+cudaError_t launch_project_tile(const FrameDev &F, int c, int count, float factor, cudaStream_t s, int *nlaunch, bool uncovered_only);
+cudaError_t configure_project_tma();
+bool project_tma_enabled();
+cudaError_t launch_project_tma(const FrameDev &F, const TileMaps &M, int c, int count, int xsel, float factor, cudaStream_t s);
 cudaError_t configure_project_tile22();
 cudaError_t launch_project_tile22(const FrameDev &F, int c, int count, float factor, cudaStream_t s, int *nlaunch);
 
@@ -321,7 +325,8 @@ static bool g_tile22 = true;
 cudaError_t configure_project_kernels() {
     const char *e = getenv("J2P_PROJ_TILE22");
     g_tile22 = !(e && *e == '0');
-    return configure_project_tile22();
+    const cudaError_t rc = configure_project_tma();
+    return rc != cudaSuccess ? rc : configure_project_tile22();
 }
 
 // strip sessions: fold the per-rank sums of g^2 in rank order (deterministic), then the norms of
@@ -370,7 +375,14 @@ cudaError_t launch_project(const FrameDev &Fin, float factor, cudaStream_t s, in
             while (c + count < F.nc && F.pl[c + count].sw == 1 && F.pl[c + count].sh == 1 && F.pl[c + count].cw == P.cw &&
                    F.pl[c + count].ch == P.ch)
                 count++;
-            const cudaError_t eb = launch_project_tile(F, c, count, factor, s, nlaunch);
+            // persistent TMA-fed kernel where the session has tensor maps; it takes the unrestricted frame
+            const bool tma = Fin.host_maps != nullptr && project_tma_enabled();
+            if (tma) {
+                const cudaError_t et = launch_project_tma(Fin, *static_cast<const TileMaps *>(Fin.host_maps), c, count, Fin.buf_sel, factor, s);
+                if (et != cudaSuccess) return et;
+                *nlaunch += 1;
+            }
+            const cudaError_t eb = launch_project_tile(F, c, count, factor, s, nlaunch, tma);
             if (eb != cudaSuccess) return eb;
             c += count - 1;
         }

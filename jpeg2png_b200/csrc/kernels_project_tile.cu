@@ -249,14 +249,18 @@ static cudaError_t launch_step_uncovered(const FrameDev &F, int c, float factor,
 
 // F: already restricted to the rows the session owns (launch_project).  Projects planes
 // c .. c+count-1, which must all be 1x1 planes with the same coefficient grid.
-cudaError_t launch_project_tile(const FrameDev &F, int c, int count, float factor, cudaStream_t s, int *nlaunch) {
+// uncovered_only: the tiles have been projected by the TMA kernel; only the stepped-only pixels remain
+cudaError_t launch_project_tile(const FrameDev &F, int c, int count, float factor, cudaStream_t s, int *nlaunch, bool uncovered_only) {
     const PlaneDev &P = F.pl[c];
     const int bw = P.cw >> 3, bh = P.ch >> 3;
     const dim3 grid((bw + 31) / 32, bh, count);
-    if (P.resample) k_project_tile<true><<<grid, PT_NT, 0, s>>>(F, c, factor);
-    else k_project_tile<false><<<grid, PT_NT, 0, s>>>(F, c, factor);
-    cudaError_t e = cudaGetLastError();
-    *nlaunch += 1;
+    cudaError_t e = cudaSuccess;
+    if (!uncovered_only) {
+        if (P.resample) k_project_tile<true><<<grid, PT_NT, 0, s>>>(F, c, factor);
+        else k_project_tile<false><<<grid, PT_NT, 0, s>>>(F, c, factor);
+        e = cudaGetLastError();
+        *nlaunch += 1;
+    }
     for (int k = c; k < c + count && e == cudaSuccess; k++)
         if (F.pl[k].cw < F.W || F.pl[k].ch < F.H) {
             e = launch_step_uncovered(F, k, factor, s);

@@ -1,0 +1,324 @@
+// kernels_project_tma.cu — step + projection of full-resolution (1x1) planes as a PERSISTENT kernel
+// fed by the Tensor Memory Accelerator.
+//
+// Arithmetic and thread mapping are those of kernels_project_tile.cu (8 threads per 8x8 block,
+// thread j owns row j, three 2-D transforms through swizzled shared-memory transposes, results
+// leave through coalesced cooperative stores).  What changes is how tiles arrive:
+//
+//   * one CTA per resident slot loops over tiles (256 x 8 pixels of one plane); tables, norms and
+//     plane descriptors are fetched once per CTA, not once per tile — the prologue latency the
+//     short-lived CTAs of the tile kernel paid 12 150 times per 4K launch is gone;
+//   * the three 8 KB arrays of tile n+1 (x_k, x_{k-1}, g) are fetched by ONE elected thread with
+//     cp.async.bulk.tensor.2d (eight 32 x 8 boxes per array) while the CTA computes tile n; the
+//     hardware 128-byte swizzle writes them in exactly the layout the compute mapping reads
+//     conflict-free (16-byte chunk index XOR row), so the 6 cp.async + address arithmetic per thread
+//     of the tile kernel disappear; the tile's 4 KB of quantised coefficients arrive with one
+//     cp.async.bulk; completion is an mbarrier transaction count, no thread waits on a copy it issued;
+//   * tensor maps are 2-D (rows x W), so a ragged right edge is zero-filled by the hardware and the
+//     loads never run past a row.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "kernels.cuh"
+#include "numerics.cuh"
+#include "project_common.cuh"
+#include "strip_sync.cuh"
+#include "tma_maps.h"
+
+namespace j2p {
+
+constexpr int TP_NT = 256;                      // 32 blocks x 8 rows
+constexpr int TP_ARRAY = 8192;                  // one staged array: 8 groups x 8 rows x 128 bytes
+constexpr int TP_STAGE = 3 * TP_ARRAY + 4096;   // x_k, x_{k-1}, g, coefficient words
+constexpr int TP_QROW = 72;                     // table stride: row j of a table starts at j*8 + (j>>2)*4 floats (rows 4..7 shifted by 16 bytes:
+                                                // the eight 16-byte reads of a block then hit eight different bank groups)
+constexpr int TP_SMEM = 2 * TP_STAGE + (TP_NT / 8) * TILE_STRIDE * 4 + 3 * 3 * TP_QROW * 4 + 64;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// wait for the phase with the given parity; a transfer that never completes traps instead of hanging the device
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap *map, int x, int y, unsigned bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_load(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+struct TileCoord {
+    int z, by, bx0, nbx;
+};
+
+// RES: the planes' coefficient grid is smaller than the frame (compute.c:338), e.g. 1080p luma
+template <bool RES>
+__global__ void __launch_bounds__(TP_NT, 3) k_project_tma(const __grid_constant__ FrameDev F, const __grid_constant__ TileMaps M, const int c0, const int count,
+                                                         const int xsel, const float factor) {
+    extern __shared__ __align__(1024) unsigned char base[];         // 128-byte swizzle: the boxes must sit on 1024-byte boundaries
+    float *tiles = reinterpret_cast<float *>(base + 2 * TP_STAGE);
+    float *sq = tiles + (TP_NT / 8) * TILE_STRIDE;                  // [plane][3][TP_QROW]
+    float *snorm = sq + 3 * 3 * TP_QROW;                            // [plane][2]
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(snorm + 8);
+    const int tid = threadIdx.x;
+    const PlaneDev &P0 = F.pl[c0];                                  // the planes of one launch share their geometry
+    const int W = F.W, bw = P0.cw >> 3, bh = P0.ch >> 3;
+    const int tx = (bw + 31) >> 5, per_plane = tx * bh, ntiles = per_plane * count;
+    const unsigned bar0 = smem_u32(bars);
+
+    auto coord = [&](int t) {
+        TileCoord q;
+        q.z = t / per_plane;
+        const int r = t - q.z * per_plane;
+        q.by = r / tx;
+        q.bx0 = (r - q.by * tx) * 32;
+        q.nbx = min(32, bw - q.bx0);
+        return q;
+    };
+    // one thread: everything tile t needs, into stage s
+    auto issue = [&](int t, int s) {
+        const TileCoord q = coord(t);
+        const int c = c0 + q.z;
+        const unsigned bar = bar0 + 8u * s, dst = smem_u32(base + s * TP_STAGE);
+        const unsigned data_bytes = (unsigned)q.nbx * 128u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // the stage was last touched through the generic proxy
+        mbar_expect_tx(bar, 3u * TP_ARRAY + data_bytes);
+        const int px = q.bx0 * 8, py = F.t0 + q.by * 8;                     // maps start at local row 0; the projection works on owned rows
+        const CUtensorMap *mx = &M.m[c][xsel], *mp = &M.m[c][xsel ^ 1], *mg = &M.m[c][2];
+#pragma unroll
+        for (int g = 0; g < 8; g++) {                                         // groups past the right edge are zero-filled (and still counted)
+            tma_load_2d(dst + g * 1024, mx, px + g * 32, py, bar);
+            tma_load_2d(dst + TP_ARRAY + g * 1024, mp, px + g * 32, py, bar);
+            tma_load_2d(dst + 2 * TP_ARRAY + g * 1024, mg, px + g * 32, py, bar);
+        }
+        bulk_load(dst + 3 * TP_ARRAY, F.pl[c].data + ((size_t)(q.by * bw + q.bx0) * 64), data_bytes, bar);
+    };
+
+    // ---- once per CTA: barriers, tables, norms -------------------------------------------------
+    if (tid == 0) {
+        if (smem_u32(base) & 1023u) __trap();                        // the swizzle pattern assumes it
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int e = tid; e < count * 192; e += TP_NT) {
+        const int z = e / 192, k = (e % 192) >> 6, i = e & 63;
+        sq[(z * 3 + k) * TP_QROW + i + ((i >> 5) << 2)] = k == 0 ? F.q[c0 + z][i] : (k == 1 ? F.qq[c0 + z][i] : F.rqq[c0 + z][i]);
+    }
+    if (tid >= 64 && tid < 96)
+        for (int z = 0; z < count; z++) strip_norm(F, c0 + z, snorm + 2 * z, tid - 64);   // whole frame: what k_gradient left; strips: fold of every rank's sums
+    __syncthreads();
+    int t = blockIdx.x;
+    if (tid == 0 && t < ntiles) issue(t, 0);
+
+    const int b = tid >> 3, j = tid & 7;
+    const unsigned gmask = 0xffu << (tid & 24);
+    float *tile = tiles + b * TILE_STRIDE;
+    const int ci0 = (b >> 2) * 64 + j * 8 + ((2 * (b & 3)) ^ j), ci1 = (b >> 2) * 64 + j * 8 + ((2 * (b & 3) + 1) ^ j);   // this thread's two 16-byte cells of an array
+
+    for (int k = 0; t < ntiles; k++, t += gridDim.x) {
+        const int s = k & 1;
+        if (tid == 0 && t + (int)gridDim.x < ntiles) issue(t + gridDim.x, s ^ 1);   // stage s^1 was released by the barrier that ended the previous tile
+        const TileCoord q = coord(t);
+        const int c = c0 + q.z;
+        const PlaneDev &P = F.pl[c];
+        float4 *sx = reinterpret_cast<float4 *>(base + s * TP_STAGE), *sp = sx + TP_ARRAY / 16, *sg = sp + TP_ARRAY / 16;
+        const int4 *sdata = reinterpret_cast<const int4 *>(sg + TP_ARRAY / 16);
+        const float *sqz = sq + q.z * 3 * TP_QROW + ((j >> 2) << 2);
+        const bool real = b < q.nbx;
+        const bool use_prob = P.use_prob != 0;
+        Stepper stepper;
+        stepper.factor = factor;
+        stepper.step = F.step;
+        stepper.norm = snorm[2 * q.z];
+        stepper.rn = snorm[2 * q.z + 1];
+        stepper.stepping = stepper.norm != 0.f;                        // compute.c:211
+        const bool norm_ok = qdiv_divisor_ok(stepper.norm);
+        Stepper2 stepper2;
+        stepper2.init(stepper, F.one);
+        mbar_wait(bar0 + 8u * s, (unsigned)(k >> 1) & 1u);
+
+        if (real) {
+            const int4 draw = sdata[b * 8 + j];
+            // ---- stepped point (compute.c:436, :213) from this thread's row of the tile --------------
+            float z[8], v[8], mean[8];
+            {
+                unsigned key = 0xffffffffu;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int ci = h ? ci1 : ci0;
+                    const float4 a = sx[ci], p = sp[ci], g = sg[ci];
+                    const f2 y01 = stepper2.fast(pk(a.x, a.y), pk(p.x, p.y), pk(g.x, g.y), key);
+                    const f2 y23 = stepper2.fast(pk(a.z, a.w), pk(p.z, p.w), pk(g.z, g.w), key);
+                    z[h * 4 + 0] = lo(y01); z[h * 4 + 1] = hi(y01); z[h * 4 + 2] = lo(y23); z[h * 4 + 3] = hi(y23);
+                }
+                if (stepper.stepping && !(norm_ok && key >= QDIV_KEY_MIN)) {   // outside the proven range: IEEE division
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int ci = h ? ci1 : ci0;
+                        const float4 a = sx[ci], p = sp[ci], g = sg[ci];
+                        z[h * 4 + 0] = stepper(a.x, p.x, g.x);
+                        z[h * 4 + 1] = stepper(a.y, p.y, g.y);
+                        z[h * 4 + 2] = stepper(a.z, p.z, g.z);
+                        z[h * 4 + 3] = stepper(a.w, p.w, g.w);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (RES) {                                             // sampling 1x1 on a coefficient grid smaller than the frame
+                    const float m = fadd(0.f, z[i]);                   // compute.c:351-359 with one sample: (0 + z) / 1
+                    mean[i] = m;
+                    v[i] = m;
+                } else {
+                    mean[i] = 0.f;
+                    v[i] = z[i];
+                }
+            }
+
+            fdct8x8_rows(v, tile, j, gmask);
+
+            // ---- clamp to the quantisation interval (compute.c:323-331); residual (compute.c:47-49) --
+            const int dw[4] = {draw.x, draw.y, draw.z, draw.w};
+            float r[8], num[8];
+            unsigned rkey = 0xffffffffu;
+            {
+                const float4 *t0 = reinterpret_cast<const float4 *>(&sqz[j * 8]);
+                const float4 *t1 = reinterpret_cast<const float4 *>(&sqz[TP_QROW + j * 8]);
+                const float4 *t2 = reinterpret_cast<const float4 *>(&sqz[2 * TP_QROW + j * 8]);
+                float qv[8], qqv[8], rqv[8];
+#pragma unroll
+                for (int k2 = 0; k2 < 2; k2++) {
+                    const float4 a = t0[k2], bq = t1[k2], cq = t2[k2];
+                    qv[k2 * 4] = a.x; qv[k2 * 4 + 1] = a.y; qv[k2 * 4 + 2] = a.z; qv[k2 * 4 + 3] = a.w;
+                    qqv[k2 * 4] = bq.x; qqv[k2 * 4 + 1] = bq.y; qqv[k2 * 4 + 2] = bq.z; qqv[k2 * 4 + 3] = bq.w;
+                    rqv[k2 * 4] = cq.x; rqv[k2 * 4 + 1] = cq.y; rqv[k2 * 4 + 2] = cq.z; rqv[k2 * 4 + 3] = cq.w;
+                }
+                const f2 one2 = splat(F.one), hf = splat(0.5f);
+#pragma unroll
+                for (int i = 0; i < 8; i += 2) {                       // two coefficients at a time (packed fp32)
+                    const int w = dw[i >> 1];
+                    const f2 d = pk(small_int_to_float((int)(short)(w & 0xffff)), small_int_to_float(w >> 16));
+                    const f2 q2 = pk(qv[i], qv[i + 1]);
+                    const f2 lo2 = mul2(sub2(d, hf), q2), hi2 = mul2(add2(d, hf), q2);
+                    float t0_ = v[i], t1_ = v[i + 1];
+                    t0_ = t0_ > lo(hi2) ? lo(hi2) : (t0_ < lo(lo2) ? lo(lo2) : t0_);
+                    t1_ = t1_ > hi(hi2) ? hi(hi2) : (t1_ < hi(lo2) ? hi(lo2) : t1_);
+                    v[i] = t0_;
+                    v[i + 1] = t1_;
+                    const f2 n2 = addm2(mul2(neg2(d), q2), pk(t0_, t1_), one2);     // t - d*q (compute.c:47)
+                    num[i] = lo(n2);
+                    num[i + 1] = hi(n2);
+                    rkey = min(rkey, min(qdiv_key(lo(n2)), qdiv_key(hi(n2))));
+                    const f2 r2 = qdiv2(n2, neg2(pk(qqv[i], qqv[i + 1])), pk(rqv[i], rqv[i + 1]));   // compute.c:49
+                    r[i] = lo(r2);
+                    r[i + 1] = hi(r2);
+                }
+                if (rkey < QDIV_KEY_MIN) {                             // a residual below 2^-60: IEEE division
+#pragma unroll
+                    for (int i = 0; i < 8; i++) r[i] = fdiv(num[i], qqv[i]);
+                }
+            }
+
+            idct8x8_rows(v, tile, j, gmask);
+            if (use_prob) idct8x8_rows(r, tile, j, gmask);
+
+            // ---- results into this thread's own cells of the stage -----------------------------------
+            if (RES) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[i] = fadd(fsub(z[i], mean[i]), v[i]);   // compute.c:390-403
+            }
+            const float pa = P.p_alpha;
+            sx[ci0] = make_float4(v[0], v[1], v[2], v[3]);
+            sx[ci1] = make_float4(v[4], v[5], v[6], v[7]);
+            if (use_prob) {
+                sp[ci0] = make_float4(fmul(pa, r[0]), fmul(pa, r[1]), fmul(pa, r[2]), fmul(pa, r[3]));   // compute.c:62
+                sp[ci1] = make_float4(fmul(pa, r[4]), fmul(pa, r[5]), fmul(pa, r[6]), fmul(pa, r[7]));
+            }
+        }
+        __syncthreads();
+
+        // ---- coalesced copy-out: x_{k+1} over x_{k-1} (compute.c:387), gp for the next iteration ----
+        const int valid_c4 = q.nbx * 2;
+        const size_t row0 = (size_t)(F.t0 + q.by * 8) * W + (size_t)q.bx0 * 8;
+        float *xout = P.xp + row0, *gp0 = P.gp + (size_t)(q.by * 8) * P.cw + (size_t)q.bx0 * 8;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const int e = tid + TP_NT * i, row = e >> 6, c4 = e & 63;
+            if (c4 < valid_c4) {
+                const int ci = (c4 >> 3) * 64 + row * 8 + ((c4 & 7) ^ row);
+                *reinterpret_cast<float4 *>(xout + (size_t)row * W + (size_t)c4 * 4) = sx[ci];
+                if (use_prob) *reinterpret_cast<float4 *>(gp0 + (size_t)row * P.cw + (size_t)c4 * 4) = sp[ci];
+            }
+        }
+        // ---- strips over peer memory: the strip's first / last two rows also go straight into the
+        // neighbours' halo rows, and the last border tile of the iteration raises their flag
+        const StripSync &S = F.sync;
+        if (S.nranks > 1 && S.fused_halo) {
+            const bool top = q.by == 0 && S.has_up, bottom = q.by == bh - 1 && S.has_down;
+            if (top || bottom) {
+                for (int e = tid; e < 4 * 64; e += TP_NT) {                   // 2 rows x 64 pieces, top then bottom
+                    const int side = e >> 7, rr = (e >> 6) & 1, c4 = e & 63;
+                    if (c4 >= valid_c4 || !(side ? bottom : top)) continue;
+                    const int row = side ? 6 + rr : rr;
+                    float *dst = (side ? S.down_dst[c] : S.up_dst[c]) + (size_t)rr * W + (size_t)q.bx0 * 8 + (size_t)c4 * 4;
+                    *reinterpret_cast<float4 *>(dst) = sx[(c4 >> 3) * 64 + row * 8 + ((c4 & 7) ^ row)];
+                }
+                if (top) strip_border_done(S, 0);
+                if (bottom) strip_border_done(S, 1);
+            }
+        }
+        __syncthreads();                                               // the stage may be refilled
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int g_tma_slots = 0;        // resident CTAs of the kernel on one device (all B200s of a box are alike)
+static bool g_tma_on = true;
+
+cudaError_t configure_project_tma() {
+    const char *e = getenv("J2P_PROJ_TMA");
+    g_tma_on = !(e && *e == '0');                                      // J2P_PROJ_TMA=0: the cp.async tile kernel (A/B aid)
+    cudaError_t rc = cudaFuncSetAttribute(k_project_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM);
+    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(k_project_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM);
+    if (rc != cudaSuccess) return rc;
+    int per_sm = 0, dev = 0, sms = 0;
+    rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_project_tma<false>, TP_NT, TP_SMEM);
+    if (rc != cudaSuccess) return rc;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    g_tma_slots = sms * (per_sm > 0 ? per_sm : 1);
+    return cudaSuccess;
+}
+
+bool project_tma_enabled() { return g_tma_on; }
+
+// F: the session's frame (NOT restricted to the owned rows: the kernel adds F.t0 itself).  Projects
+// planes c .. c+count-1, which must all be 1x1 planes with the same coefficient grid and have maps.
+cudaError_t launch_project_tma(const FrameDev &F, const TileMaps &M, int c, int count, int xsel, float factor, cudaStream_t s) {
+    const PlaneDev &P = F.pl[c];
+    const int bw = P.cw >> 3, bh = P.ch >> 3;
+    const int ntiles = ((bw + 31) / 32) * bh * count;
+    const int grid = ntiles < g_tma_slots ? ntiles : g_tma_slots;
+    if (P.resample) k_project_tma<true><<<grid, TP_NT, TP_SMEM, s>>>(F, M, c, count, xsel, factor);
+    else k_project_tma<false><<<grid, TP_NT, TP_SMEM, s>>>(F, M, c, count, xsel, factor);
+    return cudaGetLastError();
+}
+
+}  // namespace j2p

@@ -28,6 +28,30 @@ struct Stepper {
     }
 };
 
+// The same on two adjacent pixels at once (packed fp32, numerics.cuh): half the issue slots.
+//   y - step * q  ==  y + (-step) * q  bit for bit; the sum with the product goes through addm2().
+struct Stepper2 {
+    f2 fac, nstep, nnorm, rn, one;
+    bool stepping;
+    __device__ __forceinline__ void init(const Stepper &s, float one_) {
+        fac = splat(s.factor); nstep = splat(-s.step); nnorm = splat(-s.norm); rn = splat(s.rn); one = splat(one_);
+        stepping = s.stepping;
+    }
+    __device__ __forceinline__ f2 fast(f2 x, f2 xp, f2 g, unsigned &key) const {
+        f2 y = addm2(mul2(fac, sub2(x, xp)), x, one);
+        if (stepping) {
+            key = min(key, min(qdiv_key(lo(g)), qdiv_key(hi(g))));
+            y = addm2(mul2(nstep, qdiv2(g, nnorm, rn)), y, one);
+        }
+        return y;
+    }
+};
+
+// (float)d for |d| < 2^22 without the conversion pipe (XU, a quarter of the fp32 rate and the busiest
+// pipe of the projection): 1.5 * 2^23 + d is exact as an integer add on the bit pattern, and
+// subtracting 1.5 * 2^23 again is an exact fp32 subtraction.  Quantised coefficients are int16.
+__device__ __forceinline__ float small_int_to_float(int d) { return __fsub_rn(__int_as_float(0x4B400000 + d), 12582912.0f); }
+
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");

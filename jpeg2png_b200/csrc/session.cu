@@ -30,6 +30,7 @@
 #include "../../include/jpeg2png_b200.h"
 #include "copy_pool.h"
 #include "kernels.cuh"
+#include "tma_maps.h"
 
 namespace j2p {
 int grad_cta_count(int W, int H);
@@ -40,6 +41,7 @@ cudaError_t launch_fold_sums(const double *sums_by_rank, int nranks, int nc, flo
 cudaError_t launch_decode(const int16_t *data, const float *q_host, float *out, int cw, int ch, cudaStream_t s);
 cudaError_t launch_init_plane(const float *fdata, float *x, float *xp, int W, int H, int cw, int ch, int sw, int sh,
                               cudaStream_t s);
+cudaError_t launch_scanlines(const float *Y, const float *Cb, const float *Cr, int W, int w, int h, int bits, uint8_t *out, cudaStream_t s);
 // kernels_strip.cu: the strip exchanges over peer memory (parameter blocks in kernels.cuh)
 cudaError_t launch_halo_exchange(const HaloPeers &P, unsigned seq, unsigned *ticket, int *err, int wait_for_arrival, cudaStream_t s);
 }  // namespace j2p
@@ -166,6 +168,9 @@ struct j2p_session {
     cudaStream_t stream = nullptr;
     FrameDev F{};
     j2p_frame_desc desc{};
+    TileMaps maps;                    // TMA descriptors of the plane buffers (tma_maps.h)
+    float *slab = nullptr;            // x, xp, g, gp of every plane (see create_impl)
+    size_t slab_bytes = 0;
     float *x[3] = {}, *xp[3] = {}, *g[3] = {}, *gp[3] = {}, *fdata0[3] = {};
     int16_t *data[3] = {};
     bool uploaded[3] = {};
@@ -186,6 +191,16 @@ struct j2p_session {
     cudaEvent_t stage_ev[kStageSlots] = {};
     unsigned stage_next = 0;
 };
+
+// x_k <-> x_{k-1} after an iteration (reference SWAP at compute.c:438); all planes together, which
+// keeps pl[c].x == pl[0].x + c * plane_stride
+static void swap_iterates(FrameDev &F) {
+    for (int c = 0; c < F.nc; c++) {
+        PlaneDev &P = F.pl[c];
+        float *tp = P.x; P.x = P.xp; P.xp = tp;
+    }
+    F.buf_sel ^= 1;
+}
 
 template <typename T>
 static cudaError_t dev_alloc(j2p_session *s, T **p, size_t bytes) {
@@ -335,6 +350,24 @@ static int create_impl(j2p_session *s, int device, const j2p_frame_desc *d, unsi
         CK(cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming));
         s->ev_iter[i] = -1;
     }
+    // One slab holds x[0..nc), xp[0..nc), g[0..nc), gp[0..nc), every plane PS elements after the
+    // previous one of its array (gp planes are smaller than PS; the rest of their slot is unused).
+    // The gradient kernel addresses an array from one lane pointer plus c * PS (FrameDev::
+    // plane_stride), and a strip session exports ONE cudaIpc handle.
+    const size_t PS = (n + 63) & ~(size_t)63;                            // 256-byte aligned planes
+    const size_t slab_elems = PS * 4 * d->nchannel;
+    if (slab_elems > 0xffffffffull) return fail(J2P_ERR_ARG, "frame %ux%u too large for 32-bit element offsets", W, H);
+    CK(dev_alloc(s, &s->slab, slab_elems * sizeof(float)));
+    s->slab_bytes = slab_elems * sizeof(float);
+    F.slab = s->slab;
+    F.plane_stride = (unsigned)PS;
+    size_t at_x[3], at_xp[3], at_g[3], at_gp[3];
+    for (unsigned c = 0; c < d->nchannel; c++) {
+        at_x[c] = PS * (0 * d->nchannel + c);
+        at_xp[c] = PS * (1 * d->nchannel + c);
+        at_g[c] = PS * (2 * d->nchannel + c);
+        at_gp[c] = PS * (3 * d->nchannel + c);
+    }
     for (unsigned c = 0; c < d->nchannel; c++) {
         PlaneDev &P = F.pl[c];
         // coefficient rows this session holds: those whose footprint lies in the owned frame rows
@@ -348,14 +381,27 @@ static int create_impl(j2p_session *s, int device, const j2p_frame_desc *d, unsi
         P.p_alpha = d->pweight[c] * 2 * 255 * sqrtf(2);                 // compute.c:245
         P.cnt = (float)(d->w_samp[c] * d->h_samp[c]);                   // compute.c:359
         const size_t nc = (size_t)P.cw * P.ch;
-        CK(dev_alloc(s, &s->x[c], n * sizeof(float)));
-        CK(dev_alloc(s, &s->xp[c], n * sizeof(float)));
-        CK(dev_alloc(s, &s->g[c], n * sizeof(float)));
-        CK(dev_alloc(s, &s->gp[c], nc * sizeof(float)));
+        s->x[c] = s->slab + at_x[c];
+        s->xp[c] = s->slab + at_xp[c];
+        s->g[c] = s->slab + at_g[c];
+        s->gp[c] = s->slab + at_gp[c];
         CK(dev_alloc(s, &s->fdata0[c], nc * sizeof(float)));
         CK(dev_alloc(s, &s->data[c], nc * sizeof(int16_t)));
         P.x = s->x[c]; P.xp = s->xp[c]; P.g = s->g[c]; P.gp = s->gp[c]; P.data = s->data[c];
     }
+    // tensor maps for the TMA-fed projection: the two iterate buffers and the gradient of every plane
+    // that has a tiled projection kernel; a driver without the entry point leaves the cp.async kernels
+    bool maps_ok = true;
+    for (unsigned c = 0; c < d->nchannel && maps_ok; c++) {
+        const bool p11 = d->w_samp[c] == 1 && d->h_samp[c] == 1, p22 = d->w_samp[c] == 2 && d->h_samp[c] == 2;
+        if (!p11 && !p22) continue;
+        const int box_rows = p11 ? 8 : 16;
+        maps_ok = encode_plane_map(&s->maps.m[c][0], s->x[c], F.W, F.H, box_rows) == 0 &&
+                  encode_plane_map(&s->maps.m[c][1], s->xp[c], F.W, F.H, box_rows) == 0 &&
+                  encode_plane_map(&s->maps.m[c][2], s->g[c], F.W, F.H, box_rows) == 0;
+    }
+    F.host_maps = maps_ok ? &s->maps : nullptr;
+    F.buf_sel = 0;
     F.grad_ctas = grad_cta_count(F.W, F.t1 - F.t0);
     F.grad_slots = g_cfg_slots[device];
     CK(dev_alloc(s, &F.partials, sizeof(double) * 5 * (size_t)F.grad_ctas));
@@ -400,6 +446,7 @@ static int reset_impl(j2p_session *s) {
         PlaneDev &P = F.pl[c];
         P.x = s->x[c];
         P.xp = s->xp[c];
+        F.buf_sel = 0;
         // owned rows only; a strip's halo rows are filled by the driver's first halo exchange
         const size_t off = (size_t)F.t0 * F.W;
         CK(launch_init_plane(s->fdata0[c], P.x + off, P.xp + off, F.W, F.t1 - F.t0, P.cw, P.ch, P.sw, P.sh, s->stream));
@@ -556,11 +603,7 @@ static int one_iteration(j2p_session *s, cudaEvent_t e0, cudaEvent_t e1, cudaEve
     }
     if (e2) CK(cudaEventRecord(e2, s->stream));
     s->launches += 1 + (unsigned)nproj;
-    for (int c = 0; c < F.nc; c++) {                                    // compute.c:438
-        float *tmp = F.pl[c].x;
-        F.pl[c].x = F.pl[c].xp;
-        F.pl[c].xp = tmp;
-    }
+    swap_iterates(F);                                                    // compute.c:438
     return J2P_OK;
 }
 
@@ -600,11 +643,7 @@ extern "C" int j2p_session_project(j2p_session *s, const double *sums_by_rank, u
     int nproj = 0;
     CK(launch_project(F, s->pending_factor, s->stream, &nproj));
     s->launches += 1 + (unsigned)nproj;                                 // the fold kernel + the projection launches
-    for (int c = 0; c < F.nc; c++) {                                    // compute.c:438
-        float *tmp = F.pl[c].x;
-        F.pl[c].x = F.pl[c].xp;
-        F.pl[c].xp = tmp;
-    }
+    swap_iterates(F);                                                    // compute.c:438
     s->next_iter++;
     return J2P_OK;
 }
@@ -718,6 +757,23 @@ extern "C" int j2p_session_download(j2p_session *s, unsigned c, float *out) {
     return staged_d2h(s, out, s->F.pl[c].x + (size_t)s->F.t0 * s->F.W, n * sizeof(float));
 }
 
+// The reference's post-processing of a joint result (jpeg2png.c:156-159 luma += 128; png.c:39-62
+// YCbCr -> RGB, clamp, scale, truncate, 8 bit or 16 bit big-endian) on the device, delivered as PNG
+// scanlines: h rows of 1 + w*3*bits/8 bytes, each starting with filter type 0.
+extern "C" int j2p_session_download_scanlines(j2p_session *s, unsigned w, unsigned h, unsigned bits, unsigned char *out) {
+    if (!s || !out) return fail(J2P_ERR_ARG, "null argument");
+    if (s->F.nc != 3 || s->strip) return fail(J2P_ERR_ARG, "scanlines need a whole-frame session with three planes (joint mode)");
+    if (bits != 8 && bits != 16) return fail(J2P_ERR_ARG, "bits must be 8 or 16");
+    if (w == 0 || h == 0 || w > (unsigned)s->F.W || h > (unsigned)s->F.H) return fail(J2P_ERR_ARG, "image %ux%u does not fit the %dx%d frame", w, h, s->F.W, s->F.H);
+    CK(cudaSetDevice(s->device));
+    const size_t bytes = (size_t)h * ((size_t)w * 3 * (bits / 8) + 1);
+    uint8_t *dev = nullptr;
+    CK(dev_alloc(s, &dev, bytes));                   // returns to the device cache with the session
+    CK(launch_scanlines(s->F.pl[0].x, s->F.pl[1].x, s->F.pl[2].x, s->F.W, (int)w, (int)h, (int)bits, dev, s->stream));
+    s->launches++;
+    return staged_d2h(s, out, dev, bytes);
+}
+
 extern "C" int j2p_session_sync(j2p_session *s) {
     if (!s) return fail(J2P_ERR_ARG, "null session");
     CK(cudaSetDevice(s->device));
@@ -820,7 +876,8 @@ const NcclApi *nccl_api() {
 
 // What a rank publishes so that the others can map its memory (cudaIpc, same node)
 struct P2PInfo {
-    cudaIpcMemHandle_t mail, flags, x[3], xp[3];
+    cudaIpcMemHandle_t mail, flags, slab;
+    unsigned long long x_off[3], xp_off[3];      // element offsets of the two iterate buffers of every plane inside the slab
     int t0, t1, H, W, nc, ok;
 };
 
@@ -933,8 +990,11 @@ static int p2p_bind(j2p_comm *c, j2p_session *s, const NcclApi *api) {
               cudaMemset(c->mail, 0, sizeof(double) * 2 * nr * 4) == cudaSuccess &&
               cudaMemset(c->flags, 0, sizeof(unsigned) * (2 * nr + 8)) == cudaSuccess &&
               cudaIpcGetMemHandle(&mine.mail, c->mail) == cudaSuccess && cudaIpcGetMemHandle(&mine.flags, c->flags) == cudaSuccess;
-    for (int k = 0; k < F.nc && ok; k++)
-        ok = cudaIpcGetMemHandle(&mine.x[k], s->x[k]) == cudaSuccess && cudaIpcGetMemHandle(&mine.xp[k], s->xp[k]) == cudaSuccess;
+    ok = ok && cudaIpcGetMemHandle(&mine.slab, s->slab) == cudaSuccess;
+    for (int k = 0; k < F.nc; k++) {
+        mine.x_off[k] = (unsigned long long)(s->x[k] - s->slab);
+        mine.xp_off[k] = (unsigned long long)(s->xp[k] - s->slab);
+    }
     mine.ok = ok ? 1 : 0;
     cudaGetLastError();
 
@@ -961,8 +1021,9 @@ static int p2p_bind(j2p_comm *c, j2p_session *s, const NcclApi *api) {
             c->peer_flags[p] = (unsigned *)open(all[p].flags);
             const bool up = p == c->rank - 1, down = p == c->rank + 1;
             if (!up && !down) continue;
+            float *peer_slab = (float *)open(all[p].slab);
             for (int k = 0; k < F.nc && ok; k++) {
-                float *b0 = (float *)open(all[p].x[k]), *b1 = (float *)open(all[p].xp[k]);
+                float *b0 = peer_slab + all[p].x_off[k], *b1 = peer_slab + all[p].xp_off[k];
                 if (up) { c->up_buf[k][0] = b0; c->up_buf[k][1] = b1; }
                 else { c->down_buf[k][0] = b0; c->down_buf[k][1] = b1; }
             }
@@ -1138,11 +1199,7 @@ extern "C" int j2p_session_iterate_strip(j2p_session *s, j2p_comm *c, unsigned n
             CK(launch_project(F, factor, s->stream, &nproj));
             s->launches += 2 + (unsigned)nproj;                          // gradient, fold, projection launches
         }
-        for (int k = 0; k < F.nc; k++) {                                 // compute.c:438
-            float *tmp = F.pl[k].x;
-            F.pl[k].x = F.pl[k].xp;
-            F.pl[k].xp = tmp;
-        }
+        swap_iterates(F);                                                // compute.c:438
         s->next_iter++;
         if (p2p) {
             if (c->fused_halo) c->seq_halo++;                            // delivered by the projection kernels

@@ -68,3 +68,52 @@ def test_cli_refuses_to_overwrite_and_logs_csv(codecs, tmp_path):  # noqa: F811
     assert r.returncode == 0
     r = subprocess.run([exe, '-q', '-w', '0.1,0.2,0.3', str(src)], capture_output=True, text=True)           # jpeg2png.c:210-212
     assert r.returncode == 1 and 'different weights are only possible' in r.stderr
+
+
+@pytest.mark.parametrize('bits', [8, 16])
+def test_device_scanlines_match_reference_conversion(bits):
+    """j2p_session_download_scanlines: luma + 128 (jpeg2png.c:156-159) and the colour conversion /
+    truncation of png.c:39-62 on the device, against the checker's restatement applied to the
+    float planes of the SAME session.  Image 203x117 in a 208x128 frame (4:2:0); a huge -w drives
+    samples out of [0, 255] so the clamp is exercised."""
+    import ctypes as C
+    from jpeg2png_b200 import abi, synth
+    lib = abi.load_product()
+    img = synth.synth_coefs(203, 117, 8, '4:2:0', seed=11)
+    for pl in img.planes:           # exaggerate the coefficients: results leave the displayable range
+        pl.data[:] = np.clip(pl.data.astype(np.int32) * 3, -1000, 1000).astype(np.int16)
+    d = abi.FrameDesc()
+    d.nchannel = 3
+    for c, p in enumerate(img.planes):
+        d.plane_w[c], d.plane_h[c], d.w_samp[c], d.h_samp[c] = p.w, p.h, p.w_samp, p.h_samp
+        d.pweight[c] = 0.001
+    d.weight = 0.3
+    d.iterations = 6
+    s = C.c_void_p()
+    assert lib.j2p_session_create(C.byref(s), 0, C.byref(d)) == 0, lib.j2p_last_error()
+    try:
+        for c, p in enumerate(img.planes):
+            data, quant = np.ascontiguousarray(p.data), np.ascontiguousarray(p.quant)
+            assert lib.j2p_session_upload(s, c, data.ctypes.data, quant.ctypes.data, None) == 0
+        assert lib.j2p_session_iterate(s, 0, 6) == 0
+        W, Hh = lib.j2p_session_width(s), lib.j2p_session_height(s)
+        planes = []
+        for c in range(3):
+            out = np.empty((Hh, W), np.float32)
+            assert lib.j2p_session_download(s, c, out.ctypes.data) == 0
+            planes.append(out)
+        w, h = img.width, img.height
+        depth = bits // 8
+        raw = np.full(h * (w * 3 * depth + 1), 0xAA, np.uint8)
+        assert lib.j2p_session_download_scanlines(s, w, h, bits, raw.ctypes.data) == 0, lib.j2p_last_error()
+        raw = raw.reshape(h, w * 3 * depth + 1)
+        assert (raw[:, 0] == 0).all(), 'every scanline starts with filter type 0'
+        planes[0] = planes[0] + np.float32(128.0)
+        want = np.zeros(h * w * 3 * depth, np.uint8)
+        H.load_oracle().oracle_ycc_to_rgb(w, h, bits, planes[0].ctypes.data, W, planes[1].ctypes.data, W, planes[2].ctypes.data, W, want.ctypes.data)
+        want = want.reshape(h, w * 3 * depth)
+        assert (raw[:, 1:] == want).all(), f'{int((raw[:, 1:] != want).sum())} bytes differ'
+        assert want.min() == 0 and want.max() == 255, 'the case is meant to hit both clamps'
+        assert lib.j2p_session_download_scanlines(s, W + 1, h, bits, raw.ctypes.data) != 0       # larger than the frame
+    finally:
+        lib.j2p_session_destroy(s)

@@ -65,3 +65,32 @@ def test_packed_products_are_not_contracted(tmp_path):
         assert want[name][0] > 30, 'the kernel no longer uses packed fp32?'
         seen += 1
     assert seen >= 12
+
+
+def test_small_int_to_float_trick():
+    """project_common.cuh small_int_to_float: (float)d for a quantised coefficient without the
+    conversion pipe — integer add on the bit pattern of 1.5 * 2^23, then an exact fp32 subtraction.
+    Exhaustive over int16 (the coefficient type) and beyond, against numpy's conversion."""
+    import numpy as np
+    d = np.arange(-(1 << 22) + 1, 1 << 22, dtype=np.int64)
+    bits = (np.int64(0x4B400000) + d).astype(np.uint32)
+    got = bits.view(np.float32) - np.float32(12582912.0)
+    assert got.dtype == np.float32
+    assert (got == d.astype(np.float32)).all()
+    assert (np.signbit(got) == (d < 0)).all()          # and +0 for d == 0, like (float)0
+
+
+def test_product_sum_through_fma_with_one():
+    """numerics.cuh addm2: fma(m, 1, b) == RN(m + b) bit for bit (the form that keeps ptxas from
+    contracting a packed product into the sum that follows it).  fp64 has fp32's exact products
+    and sums to spare, so RN32 of the exact value is one cast away."""
+    import numpy as np
+    rng = np.random.default_rng(3)
+    m = (rng.standard_normal(2_000_000) * np.exp2(rng.integers(-40, 40, 2_000_000))).astype(np.float32)
+    b = (rng.standard_normal(2_000_000) * np.exp2(rng.integers(-40, 40, 2_000_000))).astype(np.float32)
+    b[::7] = -m[::7]                                     # exact cancellations
+    b[::11] = 0.0
+    m[::13] = 0.0
+    fma = (m.astype(np.float64) * 1.0 + b.astype(np.float64)).astype(np.float32)   # exact in fp64, one rounding
+    add = m + b
+    assert (fma.view(np.uint32) == add.view(np.uint32)).all()
