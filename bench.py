@@ -425,9 +425,9 @@ def run_product_arm(args, rank, local_rank, world):
             rate, secs = cpu_solve_rate(img, fdata, sample_it, kind, keep=ref_planes)
             # parity AT THE BENCHMARKED SIZE: the product's first `sample_it` iterations of the same
             # frame through compute(), bit for bit against what the reference just produced
-            from tests import helpers as H
-            got = H.run_compute('product', img, [0, 1, 2], WEIGHT, [PWEIGHT] * 3, sample_it, fdata)
-            same = all((H.bits(a) == H.bits(b)).all() for a, b in zip(got, ref_planes))
+            from tests import helpers as checker        # (H is the frame height in this function)
+            got = checker.run_compute('product', img, [0, 1, 2], WEIGHT, [PWEIGHT] * 3, sample_it, fdata)
+            same = all((checker.bits(a) == checker.bits(b)).all() for a, b in zip(got, ref_planes))
             parity_at_size = {'result': 'bit-identical' if same else 'MISMATCH', 'against': label,
                               'what': f'{WIDTH}x{HEIGHT} 4:4:4 joint, first {sample_it} iterations, all three planes'}
             if not same:

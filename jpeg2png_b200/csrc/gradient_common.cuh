@@ -11,6 +11,7 @@
 namespace j2p {
 
 constexpr int GM_WARPS = 4, GM_NT = GM_WARPS * 32, GM_USE = 60;
+constexpr int GM_DEPTH = 4;      // packed kernel: rows in flight per warp (cp.async ring in shared memory); a power of two
 #ifndef J2P_GRAD_MIN_CTAS
 #define J2P_GRAD_MIN_CTAS 3     // resident CTAs per SM the register allocation is bounded for (4 spills: measured slower)
 #endif

@@ -18,6 +18,11 @@
 //     "0 + gp" of compute.c:62 and the validity select;
 //   * dead sources are made harmless before the square root (norm^2 := 1, reciprocal := 0) instead
 //     of after it, which halves the selects per pixel;
+//   * rows travel through a per-warp ring in shared memory, GM_DEPTH rows ahead, filled with cp.async
+//     (every lane copies its own 8 bytes and later reads them back itself: no barrier, only
+//     cp.async.wait_group).  With the loads held in registers one row ahead, 12 warps x 2.3 KB were
+//     all an SM had in flight, and by Little's law that caps the kernel near 2.6 TB/s whatever the
+//     instruction count (both the scalar and the first packed build sat at 153 us; profiles/r02_notes.md);
 //   * for strip sessions the two exchanges of an iteration are part of the kernel (strip_sync.cuh).
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -25,6 +30,7 @@
 #include "gradient_common.cuh"
 #include "kernels.cuh"
 #include "numerics.cuh"
+#include "project_common.cuh"
 #include "strip_sync.cuh"
 
 namespace j2p {
@@ -68,15 +74,11 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient_packed(co
 
     double acc[NC];
     RowCarry<NC> A, B;
-    float2 ldx[NC], ldp[NC];      // x_k / x_{k-1} of the row after the one being formed
-    f2 pgp[NC];                   // DCT-distance term of the next target row (raw)
     f2 gmask[NC];                 // 1 where the pixel has such a term, else 0 (compute.c:58-62 footprint, pweight != 0)
 #pragma unroll
     for (int c = 0; c < NC; c++) {
         acc[c] = 0.;
-        ldx[c] = ldp[c] = make_float2(0.f, 0.f);
         A.y[c] = A.gx[c] = A.gy[c] = A.og[c] = A.tvb[c] = A.ud[c] = A.dg[c] = zero2;
-        pgp[c] = zero2;
     }
     A.ok1 = A.ok2 = true;
 
@@ -124,84 +126,89 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient_packed(co
         asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(a) : "r"(elem), "l"(base));
         return a;
     };
-    auto issue_row_loads = [&](int row) {
+    // ---- the row ring: slot (row mod GM_DEPTH) of this warp holds, per lane, x_k and x_{k-1} of `row`
+    // and the DCT-distance term of target row `row - 1` (what the step that forms row `row` consumes)
+    constexpr int NSLOT = 3 * NC;
+    __shared__ float2 ring[GM_WARPS][GM_DEPTH][NSLOT][32];
+    const unsigned ring_lane = (unsigned)__cvta_generic_to_shared(&ring[wid][0][0][lane]);
+    constexpr unsigned SLOT_BYTES = NSLOT * 32 * sizeof(float2);
+    auto cp8 = [](unsigned dst, unsigned long long src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory"); };
+    auto cp4 = [](unsigned dst, unsigned long long src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory"); };
+    // everything the step that forms `row` needs, into ring slot `slot`; one commit group per row
+    auto issue_row = [&](int row, unsigned slot) {
+        const unsigned dst = ring_lane + slot * SLOT_BYTES;
         const unsigned ro = (unsigned)min(max(row, 0), H - 1) * (unsigned)W;   // slabs are below 2^32 elements (checked at session creation)
+        const unsigned r = (unsigned)(min(max(row - 1, yb), ye - 1) - F.t0);    // target row of the gp term, as a row of the owned region
 #pragma unroll
         for (int c = 0; c < NC; c++) {
             if (GPM != 0) {
-                ldx[c] = *reinterpret_cast<const float2 *>(at(lp_x, ro + c * PS));
-                ldp[c] = *reinterpret_cast<const float2 *>(at(lp_xp, ro + c * PS));
+                cp8(dst + (2 * c) * 256, at(lp_x, ro + c * PS));
+                cp8(dst + (2 * c + 1) * 256, at(lp_xp, ro + c * PS));
             } else {
-                ldx[c] = *reinterpret_cast<const float2 *>(F.pl[c].x + (ro + (unsigned)pxc));
-                ldp[c] = *reinterpret_cast<const float2 *>(F.pl[c].xp + (ro + (unsigned)pxc));
+                cp8(dst + (2 * c) * 256, (unsigned long long)(F.pl[c].x + (ro + (unsigned)pxc)));
+                cp8(dst + (2 * c + 1) * 256, (unsigned long long)(F.pl[c].xp + (ro + (unsigned)pxc)));
             }
         }
-    };
-    // coefficient-grid row of the next target row, tracked incrementally (no per-step division)
-    int gcy[NC], grem[NC];
-#pragma unroll
-    for (int c = 0; c < NC; c++) {
-        const int r0 = yb - F.t0;                   // coefficient rows are stored from the first owned row
-        gcy[c] = GPM == 0 ? r0 / F.pl[c].sh : 0;
-        grem[c] = GPM == 0 ? r0 - gcy[c] * F.pl[c].sh : 0;
-    }
-    unsigned gp_rows_ok = 0;            // bit c: the prefetched gp row exists
-    auto issue_gp_loads = [&](int row) {   // for target rows yb, yb+1, ... in order; raw loads only
-        const unsigned r = (unsigned)(row - F.t0);                  // coefficient rows are stored from the first owned row
         if (GPM == 1) {                     // every gp plane has the frame's geometry and every target row has its gp row
 #pragma unroll
-            for (int c = 0; c < NC; c++) {
-                const float2 v = *reinterpret_cast<const float2 *>(at(lp_gp, r * (unsigned)W + c * PS));
-                pgp[c] = pk(v.x, v.y);
-            }
-            return;
-        }
-        if (GPM == 2) {                     // 4:2:0 with aligned grids: plane 0 full resolution, planes 1, 2 at half resolution
-            const bool ok0 = r < (unsigned)F.pl[0].ch;              // 1080p: luma rows 1080..1087 have no term (warp-uniform)
-            const float2 v = *reinterpret_cast<const float2 *>(at(lp_gp, (ok0 ? r : 0u) * (unsigned)W));
-            pgp[0] = pk(v.x, v.y);
+            for (int c = 0; c < NC; c++) cp8(dst + (2 * NC + c) * 256, at(lp_gp, r * (unsigned)W + c * PS));
+        } else if (GPM == 2) {              // 4:2:0 with aligned grids: plane 0 full resolution, planes 1, 2 at half resolution
+            cp8(dst + (2 * NC) * 256, at(lp_gp, min(r, (unsigned)F.pl[0].ch - 1u) * (unsigned)W));
             const unsigned rc_ = min(r >> 1, (unsigned)F.pl[1].ch - 1u) * (unsigned)(W >> 1);
 #pragma unroll
-            for (int c = 1; c < NC; c++) {
-                const float u = *reinterpret_cast<const float *>(at(lp_gpc, rc_ + c * PS));
-                pgp[c] = pk(u, u);
-            }
-            gp_rows_ok = (ok0 ? 1u : 0u) | ((r >> 1) < (unsigned)F.pl[1].ch ? 6u : 0u);
-            return;
-        }
-        gp_rows_ok = 0;
+            for (int c = 1; c < NC; c++) cp4(dst + (2 * NC + c) * 256, at(lp_gpc, rc_ + c * PS));
+        } else {
 #pragma unroll
-        for (int c = 0; c < NC; c++) {
-            const PlaneDev &P = F.pl[c];
-            const bool rowok = gcy[c] < P.ch;
-            const float *gr = P.gp + (size_t)(rowok ? gcy[c] : 0) * P.cw;
-            pgp[c] = pk(gr[gpx[c][0]], gr[gpx[c][1]]);
-            if (++grem[c] == P.sh) { grem[c] = 0; gcy[c]++; }
-            if (rowok) gp_rows_ok |= 1u << c;
+            for (int c = 0; c < NC; c++) {
+                const PlaneDev &P = F.pl[c];
+                const float *gr = P.gp + (size_t)min(r / (unsigned)P.sh, (unsigned)P.ch - 1u) * P.cw;
+                cp4(dst + (2 * NC + c) * 256, (unsigned long long)(gr + gpx[c][0]));
+                cp4(dst + (2 * NC + c) * 256 + 4, (unsigned long long)(gr + gpx[c][1]));
+            }
         }
+        cp_async_commit();
+    };
+    // which planes have a gp row for target row s (warp-uniform)
+    auto gp_rows_of = [&](int s) {
+        const unsigned r = (unsigned)(s - F.t0);
+        if (GPM == 1) return 7u;
+        if (GPM == 2) return (r < (unsigned)F.pl[0].ch ? 1u : 0u) | ((r >> 1) < (unsigned)F.pl[1].ch ? 6u : 0u);
+        unsigned ok = 0;
+#pragma unroll
+        for (int c = 0; c < NC; c++)
+            if (r / (unsigned)F.pl[c].sh < (unsigned)F.pl[c].ch) ok |= 1u << c;
+        return ok;
     };
 
     // One row step: the FISTA point of row i is formed, source row s = i-1 gets its TV and TGV
     // quotients, target row s-1 its last two addends (and is stored), target row s its first nine.
     // P: the carry of the previous step (read), N: the carry this step leaves (written).
     auto row_step = [&](const int i, const RowCarry<NC> &P, RowCarry<NC> &N) {
-        // ---- FISTA point of row i (compute.c:436) from the loads issued one step ago -----------
+        // ---- FISTA point of row i (compute.c:436) from the ring slot filled GM_DEPTH steps ago --------
+        cp_async_wait<GM_DEPTH - 1>();                          // this lane's oldest group has landed (it reads only its own bytes)
+        const unsigned slot = (unsigned)(i - (yb - 2)) & (GM_DEPTH - 1);
+        const float2 *rs = &ring[wid][slot][0][lane];
         unsigned ykey = 0xffffffffu;
 #pragma unroll
         for (int c = 0; c < NC; c++) {
-            const f2 x = pk(ldx[c].x, ldx[c].y), xp = pk(ldp[c].x, ldp[c].y);
+            const float2 vx = rs[(2 * c) * 32], vp = rs[(2 * c + 1) * 32];
+            const f2 x = pk(vx.x, vx.y), xp = pk(vp.x, vp.y);
             N.y[c] = addm2(mul2(fac, sub2(x, xp)), x, one);
             ykey = min(ykey, min(qdiv_key(lo(N.y[c])), qdiv_key(hi(N.y[c]))));
         }
         const bool ok0 = !__any_sync(0xffffffffu, ykey < QDIV_YKEY_MIN);    // one guard per VALUE (numerics.cuh, "row guard")
         N.ok1 = ok0;
         N.ok2 = P.ok1;
-        // the DCT-distance addend of target row s: 0 + gp where the pixel has one (compute.c:62), else 0
+        // the DCT-distance addend of target row s = i-1: 0 + gp where the pixel has one (compute.c:62), else 0
+        const unsigned gp_rows_ok = gp_rows_of(i - 1);
         f2 pterm[NC];
 #pragma unroll
-        for (int c = 0; c < NC; c++) pterm[c] = fma2(pgp[c], GPM == 1 || ((gp_rows_ok >> c) & 1u) ? gmask[c] : zero2, zero2);
-        issue_row_loads(i + 1);                                 // clamped: the rows too many at the end are harmless
-        if (i >= yb && i < ye) issue_gp_loads(i);               // consumed next step, where the target row is s = i
+        for (int c = 0; c < NC; c++) {
+            const float2 vg = rs[(2 * NC + c) * 32];
+            const f2 g2 = (GPM == 2 && c > 0) ? pk(vg.x, vg.x) : pk(vg.x, vg.y);   // 2x2 planes: one sample per pixel pair
+            pterm[c] = fma2(g2, (gp_rows_ok >> c) & 1u ? gmask[c] : zero2, zero2);
+        }
+        issue_row(i + GM_DEPTH, slot);                          // the slot has just been read; clamped rows at the end are harmless
 
         const int s = i - 1;
         const bool src_in = pair_in && s >= 0 && s < H;
@@ -380,11 +387,13 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient_packed(co
     // parameters only, so every shuffle is executed convergently.  Two row steps per trip with the
     // roles of the two carries swapped; an odd row count gets one idle step at the end (its loads
     // are clamped, its store is suppressed by the row test inside the step).
-    issue_row_loads(yb - 2);
+#pragma unroll
+    for (int d = 0; d < GM_DEPTH; d++) issue_row(yb - 2 + d, d);
     for (int i = yb - 2; i <= ye + 1; i += 2) {
         row_step(i, A, B);
         row_step(i + 1, B, A);
     }
+    cp_async_wait<0>();                 // nothing of this thread is in flight when it leaves
 
     // CTA reduction (fixed order => run-to-run deterministic), then the last-CTA fold
     __shared__ double red[3][GM_WARPS];

@@ -1,19 +1,25 @@
-// kernels_project_tma.cu — step + projection of full-resolution (1x1) planes as a PERSISTENT kernel
-// fed by the Tensor Memory Accelerator.
+// kernels_project_tma.cu — step + projection of full-resolution (1x1) planes as a PERSISTENT,
+// WARP-AUTONOMOUS kernel fed by the Tensor Memory Accelerator.
 //
 // Arithmetic and thread mapping are those of kernels_project_tile.cu (8 threads per 8x8 block,
-// thread j owns row j, three 2-D transforms through swizzled shared-memory transposes, results
-// leave through coalesced cooperative stores).  What changes is how tiles arrive:
+// thread j owns row j, three 2-D transforms through swizzled shared-memory transposes).  What
+// changes is the unit of work and how it arrives:
 //
-//   * one CTA per resident slot loops over tiles (256 x 8 pixels of one plane); tables, norms and
-//     plane descriptors are fetched once per CTA, not once per tile — the prologue latency the
-//     short-lived CTAs of the tile kernel paid 12 150 times per 4K launch is gone;
-//   * the three 8 KB arrays of tile n+1 (x_k, x_{k-1}, g) are fetched by ONE elected thread with
-//     cp.async.bulk.tensor.2d (eight 32 x 8 boxes per array) while the CTA computes tile n; the
-//     hardware 128-byte swizzle writes them in exactly the layout the compute mapping reads
-//     conflict-free (16-byte chunk index XOR row), so the 6 cp.async + address arithmetic per thread
-//     of the tile kernel disappear; the tile's 4 KB of quantised coefficients arrive with one
-//     cp.async.bulk; completion is an mbarrier transaction count, no thread waits on a copy it issued;
+//   * the unit is a WARP TILE: four blocks side by side (32 x 8 pixels) — what one warp computes.
+//     Every warp of the grid loops over warp tiles on its own; there is no CTA barrier anywhere in
+//     the loop (the first TMA build kept the 32-block CTA tile and its two barriers per tile: with
+//     three 8-warp CTAs per SM the barrier stalls cost more than the staging saved, 165 us against
+//     132 us for the cp.async tile kernel; profiles/r02_notes.md);
+//   * lane 0 of the warp fetches the three 1 KB arrays of its NEXT tile (x_k, x_{k-1}, g) with one
+//     cp.async.bulk.tensor.2d each (box 32 x 8 floats, SASS UTMALDG.2D) and the tile's 512 bytes of
+//     quantised coefficients with one cp.async.bulk (UBLKCP) while the warp computes the current
+//     tile; completion is an mbarrier transaction count per warp and stage.  The hardware 128-byte
+//     swizzle writes each array in exactly the layout the compute mapping reads conflict-free
+//     (16-byte chunk index XOR row);
+//   * tables, norms and plane constants are fetched once per CTA into shared memory — the
+//     dynamic-index plane descriptor in the constant bank was the hottest stall site of both
+//     earlier kernels;
+//   * results return through the stage (own cells) and leave as full 128-byte row segments;
 //   * tensor maps are 2-D (rows x W), so a ragged right edge is zero-filled by the hardware and the
 //     loads never run past a row.
 #include <cuda.h>
@@ -29,12 +35,23 @@
 
 namespace j2p {
 
-constexpr int TP_NT = 256;                      // 32 blocks x 8 rows
-constexpr int TP_ARRAY = 8192;                  // one staged array: 8 groups x 8 rows x 128 bytes
-constexpr int TP_STAGE = 3 * TP_ARRAY + 4096;   // x_k, x_{k-1}, g, coefficient words
-constexpr int TP_QROW = 72;                     // table stride: row j of a table starts at j*8 + (j>>2)*4 floats (rows 4..7 shifted by 16 bytes:
-                                                // the eight 16-byte reads of a block then hit eight different bank groups)
-constexpr int TP_SMEM = 2 * TP_STAGE + (TP_NT / 8) * TILE_STRIDE * 4 + 3 * 3 * TP_QROW * 4 + 64;
+constexpr int TP_WARPS = 4, TP_NT = TP_WARPS * 32;   // four independent warps per CTA (they share the tables)
+constexpr int TP_ARRAY = 1024;                       // one staged array of a warp tile: 8 rows x 128 bytes
+constexpr int TP_WARP_STAGE = 2 * 3 * TP_ARRAY + 2 * 512;   // two stages of x_k, x_{k-1}, g (1024-byte aligned), then two of coefficient words
+constexpr int TP_QROW = 72;                          // table stride: row j of a table starts at j*8 + (j>>2)*4 floats (rows 4..7 shifted by
+                                                     // 16 bytes: the eight 16-byte reads of a block then hit eight different bank groups)
+struct PlaneInfo {                                   // what a warp needs per tile, in shared memory
+    float *xp, *gp;
+    const int16_t *data;
+    float p_alpha;
+    int use_prob;
+};
+constexpr int TP_OFF_TILES = TP_WARPS * TP_WARP_STAGE;
+constexpr int TP_OFF_SQ = TP_OFF_TILES + TP_WARPS * 4 * TILE_STRIDE * 4;
+constexpr int TP_OFF_NORM = TP_OFF_SQ + 3 * 3 * TP_QROW * 4;
+constexpr int TP_OFF_INFO = TP_OFF_NORM + 32;
+constexpr int TP_OFF_BARS = TP_OFF_INFO + 3 * 32;
+constexpr int TP_SMEM = TP_OFF_BARS + TP_WARPS * 2 * 8;
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -65,52 +82,62 @@ struct TileCoord {
     int z, by, bx0, nbx;
 };
 
+// strips: a border warp tile has stored its rows into the neighbour (strip_sync.cuh, warp-level variant)
+__device__ __forceinline__ void strip_border_done_warp(const StripSync &S, int side, int lane) {
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) {
+        const unsigned n = atomicAdd(S.border_ticket + side, 1u) + 1u;
+        if (n == S.border_ctas[side]) {
+            S.border_ticket[side] = 0u;
+            __threadfence_system();
+            st_release_sys(side == 0 ? S.up_flag : S.down_flag, S.halo_seq + 1u);
+        }
+    }
+}
+
 // RES: the planes' coefficient grid is smaller than the frame (compute.c:338), e.g. 1080p luma
 template <bool RES>
-__global__ void __launch_bounds__(TP_NT, 3) k_project_tma(const __grid_constant__ FrameDev F, const __grid_constant__ TileMaps M, const int c0, const int count,
+__global__ void __launch_bounds__(TP_NT, 6) k_project_tma(const __grid_constant__ FrameDev F, const __grid_constant__ TileMaps M, const int c0, const int count,
                                                          const int xsel, const float factor) {
     extern __shared__ __align__(1024) unsigned char base[];         // 128-byte swizzle: the boxes must sit on 1024-byte boundaries
-    float *tiles = reinterpret_cast<float *>(base + 2 * TP_STAGE);
-    float *sq = tiles + (TP_NT / 8) * TILE_STRIDE;                  // [plane][3][TP_QROW]
-    float *snorm = sq + 3 * 3 * TP_QROW;                            // [plane][2]
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(snorm + 8);
-    const int tid = threadIdx.x;
-    const PlaneDev &P0 = F.pl[c0];                                  // the planes of one launch share their geometry
-    const int W = F.W, bw = P0.cw >> 3, bh = P0.ch >> 3;
-    const int tx = (bw + 31) >> 5, per_plane = tx * bh, ntiles = per_plane * count;
-    const unsigned bar0 = smem_u32(bars);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float *sq = reinterpret_cast<float *>(base + TP_OFF_SQ);          // [plane][3][TP_QROW]
+    float *snorm = reinterpret_cast<float *>(base + TP_OFF_NORM);     // [plane][2]
+    PlaneInfo *sinfo = reinterpret_cast<PlaneInfo *>(base + TP_OFF_INFO);
+    const PlaneDev &P0 = F.pl[c0];                                    // the planes of one launch share their geometry
+    const int W = F.W, cw = P0.cw, bw = cw >> 3, bh = P0.ch >> 3;
+    const int tw = (bw + 3) >> 2, per_plane = tw * bh, ntiles = per_plane * count;
+    unsigned char *wbase = base + wid * TP_WARP_STAGE;
+    const unsigned bar0 = smem_u32(base + TP_OFF_BARS) + 16u * wid;
 
     auto coord = [&](int t) {
         TileCoord q;
         q.z = t / per_plane;
         const int r = t - q.z * per_plane;
-        q.by = r / tx;
-        q.bx0 = (r - q.by * tx) * 32;
-        q.nbx = min(32, bw - q.bx0);
+        q.by = r / tw;
+        q.bx0 = (r - q.by * tw) * 4;
+        q.nbx = min(4, bw - q.bx0);
         return q;
     };
-    // one thread: everything tile t needs, into stage s
+    // lane 0: everything warp tile t needs, into stage s of this warp
     auto issue = [&](int t, int s) {
         const TileCoord q = coord(t);
         const int c = c0 + q.z;
-        const unsigned bar = bar0 + 8u * s, dst = smem_u32(base + s * TP_STAGE);
+        const unsigned bar = bar0 + 8u * s, dst = smem_u32(wbase + s * 3 * TP_ARRAY), ddst = smem_u32(wbase + 6 * TP_ARRAY + s * 512);
         const unsigned data_bytes = (unsigned)q.nbx * 128u;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // the stage was last touched through the generic proxy
         mbar_expect_tx(bar, 3u * TP_ARRAY + data_bytes);
         const int px = q.bx0 * 8, py = F.t0 + q.by * 8;                     // maps start at local row 0; the projection works on owned rows
-        const CUtensorMap *mx = &M.m[c][xsel], *mp = &M.m[c][xsel ^ 1], *mg = &M.m[c][2];
-#pragma unroll
-        for (int g = 0; g < 8; g++) {                                         // groups past the right edge are zero-filled (and still counted)
-            tma_load_2d(dst + g * 1024, mx, px + g * 32, py, bar);
-            tma_load_2d(dst + TP_ARRAY + g * 1024, mp, px + g * 32, py, bar);
-            tma_load_2d(dst + 2 * TP_ARRAY + g * 1024, mg, px + g * 32, py, bar);
-        }
-        bulk_load(dst + 3 * TP_ARRAY, F.pl[c].data + ((size_t)(q.by * bw + q.bx0) * 64), data_bytes, bar);
+        tma_load_2d(dst, &M.m[c][xsel], px, py, bar);                        // columns past the right edge are zero-filled (and still counted)
+        tma_load_2d(dst + TP_ARRAY, &M.m[c][xsel ^ 1], px, py, bar);
+        tma_load_2d(dst + 2 * TP_ARRAY, &M.m[c][2], px, py, bar);
+        bulk_load(ddst, sinfo[q.z].data + ((size_t)(q.by * bw + q.bx0) * 64), data_bytes, bar);
     };
 
-    // ---- once per CTA: barriers, tables, norms -------------------------------------------------
-    if (tid == 0) {
-        if (smem_u32(base) & 1023u) __trap();                        // the swizzle pattern assumes it
+    // ---- once per CTA: barriers, tables, norms, plane constants ---------------------------------
+    if (tid == 0 && (smem_u32(base) & 1023u)) __trap();              // the swizzle pattern assumes the alignment
+    if (lane == 0) {
         mbar_init(bar0, 1);
         mbar_init(bar0 + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -119,28 +146,39 @@ __global__ void __launch_bounds__(TP_NT, 3) k_project_tma(const __grid_constant_
         const int z = e / 192, k = (e % 192) >> 6, i = e & 63;
         sq[(z * 3 + k) * TP_QROW + i + ((i >> 5) << 2)] = k == 0 ? F.q[c0 + z][i] : (k == 1 ? F.qq[c0 + z][i] : F.rqq[c0 + z][i]);
     }
-    if (tid >= 64 && tid < 96)
-        for (int z = 0; z < count; z++) strip_norm(F, c0 + z, snorm + 2 * z, tid - 64);   // whole frame: what k_gradient left; strips: fold of every rank's sums
+    if (tid < count) {
+        const PlaneDev &P = F.pl[c0 + tid];
+        sinfo[tid].xp = P.xp;
+        sinfo[tid].gp = P.gp;
+        sinfo[tid].data = P.data;
+        sinfo[tid].p_alpha = P.p_alpha;
+        sinfo[tid].use_prob = P.use_prob;
+    }
+    if (wid == TP_WARPS - 1)
+        for (int z = 0; z < count; z++) strip_norm(F, c0 + z, snorm + 2 * z, lane);   // whole frame: what k_gradient left; strips: fold of every rank's sums
     __syncthreads();
-    int t = blockIdx.x;
-    if (tid == 0 && t < ntiles) issue(t, 0);
 
-    const int b = tid >> 3, j = tid & 7;
-    const unsigned gmask = 0xffu << (tid & 24);
-    float *tile = tiles + b * TILE_STRIDE;
-    const int ci0 = (b >> 2) * 64 + j * 8 + ((2 * (b & 3)) ^ j), ci1 = (b >> 2) * 64 + j * 8 + ((2 * (b & 3) + 1) ^ j);   // this thread's two 16-byte cells of an array
+    const int gw = blockIdx.x * TP_WARPS + wid, nw = gridDim.x * TP_WARPS;
+    int t = gw;
+    if (lane == 0 && t < ntiles) issue(t, 0);
 
-    for (int k = 0; t < ntiles; k++, t += gridDim.x) {
+    const int b = lane >> 3, j = lane & 7;
+    const unsigned gmask = 0xffu << (lane & 24);
+    float *tile = reinterpret_cast<float *>(base + TP_OFF_TILES) + (wid * 4 + b) * TILE_STRIDE;
+    const int ci0 = j * 8 + ((2 * b) ^ j), ci1 = j * 8 + ((2 * b + 1) ^ j);   // this thread's two 16-byte cells of an array
+    const StripSync &S = F.sync;
+
+    for (int k = 0; t < ntiles; k++, t += nw) {
         const int s = k & 1;
-        if (tid == 0 && t + (int)gridDim.x < ntiles) issue(t + gridDim.x, s ^ 1);   // stage s^1 was released by the barrier that ended the previous tile
+        if (lane == 0 && t + nw < ntiles) issue(t + nw, s ^ 1);          // stage s^1 was released by the __syncwarp that ended the previous tile
         const TileCoord q = coord(t);
         const int c = c0 + q.z;
-        const PlaneDev &P = F.pl[c];
-        float4 *sx = reinterpret_cast<float4 *>(base + s * TP_STAGE), *sp = sx + TP_ARRAY / 16, *sg = sp + TP_ARRAY / 16;
-        const int4 *sdata = reinterpret_cast<const int4 *>(sg + TP_ARRAY / 16);
+        const PlaneInfo info = sinfo[q.z];
+        float4 *sx = reinterpret_cast<float4 *>(wbase + s * 3 * TP_ARRAY), *sp = sx + TP_ARRAY / 16, *sg = sp + TP_ARRAY / 16;
+        const int4 *sdata = reinterpret_cast<const int4 *>(wbase + 6 * TP_ARRAY + s * 512);
         const float *sqz = sq + q.z * 3 * TP_QROW + ((j >> 2) << 2);
         const bool real = b < q.nbx;
-        const bool use_prob = P.use_prob != 0;
+        const bool use_prob = info.use_prob != 0;
         Stepper stepper;
         stepper.factor = factor;
         stepper.step = F.step;
@@ -153,7 +191,7 @@ __global__ void __launch_bounds__(TP_NT, 3) k_project_tma(const __grid_constant_
         mbar_wait(bar0 + 8u * s, (unsigned)(k >> 1) & 1u);
 
         if (real) {
-            const int4 draw = sdata[b * 8 + j];
+            const int4 draw = sdata[lane];
             // ---- stepped point (compute.c:436, :213) from this thread's row of the tile --------------
             float z[8], v[8], mean[8];
             {
@@ -242,7 +280,7 @@ __global__ void __launch_bounds__(TP_NT, 3) k_project_tma(const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < 8; i++) v[i] = fadd(fsub(z[i], mean[i]), v[i]);   // compute.c:390-403
             }
-            const float pa = P.p_alpha;
+            const float pa = info.p_alpha;
             sx[ci0] = make_float4(v[0], v[1], v[2], v[3]);
             sx[ci1] = make_float4(v[4], v[5], v[6], v[7]);
             if (use_prob) {
@@ -250,39 +288,36 @@ __global__ void __launch_bounds__(TP_NT, 3) k_project_tma(const __grid_constant_
                 sp[ci1] = make_float4(fmul(pa, r[4]), fmul(pa, r[5]), fmul(pa, r[6]), fmul(pa, r[7]));
             }
         }
-        __syncthreads();
+        __syncwarp();
 
-        // ---- coalesced copy-out: x_{k+1} over x_{k-1} (compute.c:387), gp for the next iteration ----
-        const int valid_c4 = q.nbx * 2;
-        const size_t row0 = (size_t)(F.t0 + q.by * 8) * W + (size_t)q.bx0 * 8;
-        float *xout = P.xp + row0, *gp0 = P.gp + (size_t)(q.by * 8) * P.cw + (size_t)q.bx0 * 8;
+        // ---- copy-out, 128 contiguous bytes per row: x_{k+1} over x_{k-1} (compute.c:387), gp for the next iteration
+        const int valid_c = q.nbx * 2, ch = lane & 7;
+        float *xout = info.xp + (size_t)(F.t0 + q.by * 8) * W + (size_t)q.bx0 * 8 + ch * 4;
+        float *gpo = info.gp + (size_t)(q.by * 8) * cw + (size_t)q.bx0 * 8 + ch * 4;
+        if (ch < valid_c) {
 #pragma unroll
-        for (int i = 0; i < 2; i++) {
-            const int e = tid + TP_NT * i, row = e >> 6, c4 = e & 63;
-            if (c4 < valid_c4) {
-                const int ci = (c4 >> 3) * 64 + row * 8 + ((c4 & 7) ^ row);
-                *reinterpret_cast<float4 *>(xout + (size_t)row * W + (size_t)c4 * 4) = sx[ci];
-                if (use_prob) *reinterpret_cast<float4 *>(gp0 + (size_t)row * P.cw + (size_t)c4 * 4) = sp[ci];
+            for (int h = 0; h < 2; h++) {
+                const int row = (lane >> 3) + 4 * h, ci = row * 8 + (ch ^ row);
+                *reinterpret_cast<float4 *>(xout + (size_t)row * W) = sx[ci];
+                if (use_prob) *reinterpret_cast<float4 *>(gpo + (size_t)row * cw) = sp[ci];
             }
         }
         // ---- strips over peer memory: the strip's first / last two rows also go straight into the
         // neighbours' halo rows, and the last border tile of the iteration raises their flag
-        const StripSync &S = F.sync;
         if (S.nranks > 1 && S.fused_halo) {
             const bool top = q.by == 0 && S.has_up, bottom = q.by == bh - 1 && S.has_down;
             if (top || bottom) {
-                for (int e = tid; e < 4 * 64; e += TP_NT) {                   // 2 rows x 64 pieces, top then bottom
-                    const int side = e >> 7, rr = (e >> 6) & 1, c4 = e & 63;
-                    if (c4 >= valid_c4 || !(side ? bottom : top)) continue;
+                const int rr = (lane >> 3) & 1, side = lane >> 4;          // lanes 0..15: top rows 0, 1; lanes 16..31: bottom rows 6, 7
+                if (ch < valid_c && (side ? bottom : top)) {
                     const int row = side ? 6 + rr : rr;
-                    float *dst = (side ? S.down_dst[c] : S.up_dst[c]) + (size_t)rr * W + (size_t)q.bx0 * 8 + (size_t)c4 * 4;
-                    *reinterpret_cast<float4 *>(dst) = sx[(c4 >> 3) * 64 + row * 8 + ((c4 & 7) ^ row)];
+                    float *dst = (side ? S.down_dst[c] : S.up_dst[c]) + (size_t)rr * W + (size_t)q.bx0 * 8 + ch * 4;
+                    *reinterpret_cast<float4 *>(dst) = sx[row * 8 + (ch ^ row)];
                 }
-                if (top) strip_border_done(S, 0);
-                if (bottom) strip_border_done(S, 1);
+                if (top) strip_border_done_warp(S, 0, lane);
+                if (bottom) strip_border_done_warp(S, 1, lane);
             }
         }
-        __syncthreads();                                               // the stage may be refilled
+        __syncwarp();                                                  // the stage may be refilled
     }
 }
 
@@ -309,13 +344,17 @@ cudaError_t configure_project_tma() {
 
 bool project_tma_enabled() { return g_tma_on; }
 
+// how many units of plane P call strip_border_done per side and iteration (session.cu counts them)
+int project_tma_border_units(const PlaneDev &P) { return ((P.cw >> 3) + 3) / 4; }
+
 // F: the session's frame (NOT restricted to the owned rows: the kernel adds F.t0 itself).  Projects
 // planes c .. c+count-1, which must all be 1x1 planes with the same coefficient grid and have maps.
 cudaError_t launch_project_tma(const FrameDev &F, const TileMaps &M, int c, int count, int xsel, float factor, cudaStream_t s) {
     const PlaneDev &P = F.pl[c];
     const int bw = P.cw >> 3, bh = P.ch >> 3;
-    const int ntiles = ((bw + 31) / 32) * bh * count;
-    const int grid = ntiles < g_tma_slots ? ntiles : g_tma_slots;
+    const int ntiles = ((bw + 3) / 4) * bh * count;                    // warp tiles
+    const int ctas = (ntiles + TP_WARPS - 1) / TP_WARPS;
+    const int grid = ctas < g_tma_slots ? ctas : g_tma_slots;
     if (P.resample) k_project_tma<true><<<grid, TP_NT, TP_SMEM, s>>>(F, M, c, count, xsel, factor);
     else k_project_tma<false><<<grid, TP_NT, TP_SMEM, s>>>(F, M, c, count, xsel, factor);
     return cudaGetLastError();

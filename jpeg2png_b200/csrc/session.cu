@@ -41,6 +41,8 @@ cudaError_t launch_fold_sums(const double *sums_by_rank, int nranks, int nc, flo
 cudaError_t launch_decode(const int16_t *data, const float *q_host, float *out, int cw, int ch, cudaStream_t s);
 cudaError_t launch_init_plane(const float *fdata, float *x, float *xp, int W, int H, int cw, int ch, int sw, int sh,
                               cudaStream_t s);
+bool project_tma_enabled();
+int project_tma_border_units(const PlaneDev &P);
 cudaError_t launch_scanlines(const float *Y, const float *Cb, const float *Cr, int W, int w, int h, int bits, uint8_t *out, cudaStream_t s);
 // kernels_strip.cu: the strip exchanges over peer memory (parameter blocks in kernels.cuh)
 cudaError_t launch_halo_exchange(const HaloPeers &P, unsigned seq, unsigned *ticket, int *err, int wait_for_arrival, cudaStream_t s);
@@ -1054,7 +1056,9 @@ static int p2p_bind(j2p_comm *c, j2p_session *s, const NcclApi *api) {
             const PlaneDev &P = F.pl[k];
             const bool tiled = (P.sw == 1 && P.sh == 1) || (P.sw == 2 && P.sh == 2);
             fused = fused && tiled && P.cw * P.sw == F.W;
-            ctas += (unsigned)(((P.cw >> 3) + (P.sw == 1 ? 31 : 15)) / (P.sw == 1 ? 32 : 16));   // tiles per block row (kernels_project_tile*.cu)
+            // units of work per block row that deliver border rows: warp tiles of the TMA kernel, CTA tiles of the cp.async kernels
+            if (P.sw == 1 && F.host_maps && project_tma_enabled()) ctas += (unsigned)project_tma_border_units(P);
+            else ctas += (unsigned)(((P.cw >> 3) + (P.sw == 1 ? 31 : 15)) / (P.sw == 1 ? 32 : 16));
         }
         const char *e = getenv("J2P_STRIP_FUSED_HALO");
         if (e && *e == '0') fused = false;
