@@ -10,10 +10,16 @@
 
 namespace j2p {
 
-constexpr int GM_WARPS = 4, GM_NT = GM_WARPS * 32, GM_USE = 60;
+#ifndef J2P_GM_WARPS
+#define J2P_GM_WARPS 4
+#endif
+constexpr int GM_WARPS = J2P_GM_WARPS, GM_NT = GM_WARPS * 32, GM_USE = 60;
 constexpr int GM_DEPTH = 4;      // packed kernel: rows in flight per warp (cp.async ring in shared memory); a power of two
 #ifndef J2P_GRAD_MIN_CTAS
-#define J2P_GRAD_MIN_CTAS 3     // resident CTAs per SM the register allocation is bounded for (4 spills: measured slower)
+#define J2P_GRAD_MIN_CTAS 2     // resident CTAs per SM the register allocation is bounded for.  Measured on the one-block row step at 4K
+                                // (profiles/r02_ab_gradient_geometry.txt): 2 CTAs (194 registers, 8 warps/SM) 117.6 us, 3 CTAs (162 registers,
+                                // 12 warps) 123.3 us, 4 CTAs (128 registers, spills) 134.9 us — the kernel is bound by dependency latency, and
+                                // registers for the scheduler to overlap chains buy more than resident warps do
 #endif
 
 // IEEE fallbacks of the two quotient stages, for rows the guards reject (numerics.cuh).  Out of line

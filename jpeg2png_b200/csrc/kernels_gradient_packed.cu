@@ -183,6 +183,15 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient_packed(co
     // One row step: the FISTA point of row i is formed, source row s = i-1 gets its TV and TGV
     // quotients, target row s-1 its last two addends (and is stored), target row s its first nine.
     // P: the carry of the previous step (read), N: the carry this step leaves (written).
+    //
+    // The whole step is ONE basic block plus one cold fix-up: the differences and both norms first,
+    // then a single vote over every guard of the row (FISTA values, both square-root arguments), then
+    // both quotient stages on the fast sequences, unconditionally.  A row the vote rejects recomputes
+    // both stages with the IEEE instructions afterwards and overrides the results (tv_slow / tgv_slow,
+    // out of line).  The earlier build voted and branched per stage (three votes and two
+    // fast/slow diamonds per row, plus a branch around the store): the scheduler could not move the
+    // TGV arithmetic under the latency of the TV square root and reciprocal, and "wait" (fixed-latency
+    // dependency) was the top stall at three warps per scheduler (profiles/r02_notes.md).
     auto row_step = [&](const int i, const RowCarry<NC> &P, RowCarry<NC> &N) {
         // ---- FISTA point of row i (compute.c:436) from the ring slot filled GM_DEPTH steps ago --------
         cp_async_wait<GM_DEPTH - 1>();                          // this lane's oldest group has landed (it reads only its own bytes)
@@ -196,9 +205,6 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient_packed(co
             N.y[c] = addm2(mul2(fac, sub2(x, xp)), x, one);
             ykey = min(ykey, min(qdiv_key(lo(N.y[c])), qdiv_key(hi(N.y[c]))));
         }
-        const bool ok0 = !__any_sync(0xffffffffu, ykey < QDIV_YKEY_MIN);    // one guard per VALUE (numerics.cuh, "row guard")
-        N.ok1 = ok0;
-        N.ok2 = P.ok1;
         // the DCT-distance addend of target row s = i-1: 0 + gp where the pixel has one (compute.c:62), else 0
         const unsigned gp_rows_ok = gp_rows_of(i - 1);
         f2 pterm[NC];
@@ -211,13 +217,13 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient_packed(co
         issue_row(i + GM_DEPTH, slot);                          // the slot has just been read; clamped rows at the end are harmless
 
         const int s = i - 1;
-        const bool src_in = pair_in && s >= 0 && s < H;
+        const bool src_in = pair_in & (s >= 0) & (s < H);
         // No row below the frame's last row: gy := 0 (compute.c:81).  Nothing to do for it: the row
         // loads are clamped into the buffer, whose last row IS the frame's last row whenever that
         // row is reachable, so row s+1 re-reads row s and gy comes out +0.
 
-        // ---- source row s: TV (compute.c:79-105) -------------------------------------------
-        f2 gx0[NC], gy0[NC], tvs0[NC], tvr0[NC];
+        // ---- source row s: first differences and the TV norm (compute.c:79-89) ----------------
+        f2 gx0[NC], gy0[NC];
         f2 n1 = zero2;
 #pragma unroll
         for (int c = 0; c < NC; c++) {
@@ -230,52 +236,14 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient_packed(co
             N.gx[c] = gx0[c];
             N.gy[c] = gy0[c];
         }
-        {
-            const bool l0 = src_in && lo(n1) != 0.f, l1 = src_in && hi(n1) != 0.f;   // sqrtf(x) != 0  <=>  x != 0   (compute.c:97)
-            const f2 ss = pk(l0 ? lo(n1) : 1.f, l1 ? hi(n1) : 1.f);                  // dead source: norm 1, reciprocal 0 => every quotient exactly 0
-            const bool fast = ok0 && P.ok1 && !__any_sync(0xffffffffu, !root_arg_ok(lo(ss)) || !root_arg_ok(hi(ss)));
-            if (__builtin_expect(fast, true)) {
-                const f2 n = sqrt2_core(ss), nb = neg2(n);
-                const f2 yr = rcp2_core(n, nb);
-                const f2 y = pk(l0 ? lo(yr) : 0.f, l1 ? hi(yr) : 0.f);
-#pragma unroll
-                for (int c = 0; c < NC; c++) {
-                    tvs0[c] = qdiv2(mul2(a1n, add2(gx0[c], gy0[c])), nb, y);   // compute.c:98: (a1 * -(gx+gy)) / n
-                    tvr0[c] = qdiv2(mul2(a1s, gx0[c]), nb, y);                  // compute.c:100
-                    N.tvb[c] = qdiv2(mul2(a1s, gy0[c]), nb, y);                 // compute.c:103
-                }
-            } else {                                                    // outside the proven range: IEEE square root and division
-                TvSlow<NC> io;
-#pragma unroll
-                for (int c = 0; c < NC; c++) {
-                    io.gx[c][0] = lo(gx0[c]); io.gx[c][1] = hi(gx0[c]);
-                    io.gy[c][0] = lo(gy0[c]); io.gy[c][1] = hi(gy0[c]);
-                }
-                tv_slow<NC>(&io, F.a1, src_in);
-#pragma unroll
-                for (int c = 0; c < NC; c++) {
-                    tvs0[c] = pk(settle(io.q[0][c][0], zero), settle(io.q[0][c][1], zero));
-                    tvr0[c] = pk(settle(io.q[1][c][0], zero), settle(io.q[1][c][1], zero));
-                    N.tvb[c] = pk(settle(io.q[2][c][0], zero), settle(io.q[2][c][1], zero));
-                }
-            }
-        }
+        const bool tl0 = src_in & (lo(n1) != 0.f), tl1 = src_in & (hi(n1) != 0.f);     // sqrtf(x) != 0  <=>  x != 0   (compute.c:97)
+        const f2 ss1 = pk(tl0 ? lo(n1) : 1.f, tl1 ? hi(n1) : 1.f);                   // dead source: norm 1, reciprocal 0 => every quotient exactly 0
+        bool bad = (ykey < QDIV_YKEY_MIN) | !root_arg_ok(lo(ss1)) | !root_arg_ok(hi(ss1));   // one guard per VALUE (numerics.cuh, "row guard")
 
-        // ---- target row s: addends 1..6 (DCT distance; TV above, left, self; TGV above, above-right)
-        f2 oA[NC];
-#pragma unroll
-        for (int c = 0; c < NC; c++) {
-            const float tvr_l = __shfl_up_sync(0xffffffffu, hi(tvr0[c]), 1);
-            f2 o = add2(add2(add2(pterm[c], P.tvb[c]), shl_from_left(tvr0[c], tvr_l)), tvs0[c]);
-            if (TGV) {
-                const float dg_r = __shfl_down_sync(0xffffffffu, lo(P.dg[c]), 1);
-                o = add2(addm2(P.ud[c], o, one), shr_from_right(P.dg[c], dg_r));
-            }
-            oA[c] = o;
-        }
-
-        // ---- source row s: second-order TGV (compute.c:136-183) ----------------------------
-        f2 t2s0[NC], lr0[NC];
+        // ---- source row s: second differences and the TGV norm (compute.c:136-152) ------------
+        f2 gxx[NC], gyy[NC], sym[NC];
+        f2 ss2 = zero2;
+        bool gl0 = false, gl1 = false;
         if (TGV) {
             f2 gyPv[NC];
 #pragma unroll
@@ -286,7 +254,6 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient_packed(co
 #pragma unroll
                 for (int c = 0; c < NC; c++) gyPv[c] = gy0[c];
             }
-            f2 gxx[NC], gyy[NC], sym[NC];
             f2 n2 = zero2;
 #pragma unroll
             for (int c = 0; c < NC; c++) {
@@ -306,24 +273,68 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient_packed(co
                 const f2 t = addm2(mul2(gyy[c], gyy[c]), addm2(mul2(u, sym[c]), mul2(gxx[c], gxx[c]), one), one);
                 n2 = c == 0 ? t : add2(n2, t);              // 0 + t == t: t is never -0
             }
-            const bool l0 = src_in && lo(n2) != 0.f, l1 = src_in && hi(n2) != 0.f;   // compute.c:158
-            const f2 ss = pk(l0 ? lo(n2) : 1.f, l1 ? hi(n2) : 1.f);
-            const bool fast = ok0 && P.ok1 && P.ok2 && !__any_sync(0xffffffffu, !root_arg_ok(lo(ss)) || !root_arg_ok(hi(ss)));
-            if (__builtin_expect(fast, true)) {
-                const f2 n = sqrt2_core(ss), nb = neg2(n);
-                const f2 yr = rcp2_core(n, nb);
-                const f2 y = pk(l0 ? lo(yr) : 0.f, l1 ? hi(yr) : 0.f);
+            gl0 = src_in & (lo(n2) != 0.f);                  // compute.c:158
+            gl1 = src_in & (hi(n2) != 0.f);
+            ss2 = pk(gl0 ? lo(n2) : 1.f, gl1 ? hi(n2) : 1.f);
+            bad = bad | !root_arg_ok(lo(ss2)) | !root_arg_ok(hi(ss2));
+        }
+
+        // ---- the row's one vote; the guard window covers the three rows the differences span ----
+        const bool ok0 = !__any_sync(0xffffffffu, bad);
+        N.ok1 = ok0;
+        N.ok2 = P.ok1;
+        const bool fast = ok0 && P.ok1 && P.ok2;
+
+        // ---- TV quotients (compute.c:97-105), fast sequences --------------------------------
+        f2 tvs0[NC], tvr0[NC], t2s0[NC], lr0[NC];
+        {
+            const f2 n = sqrt2_core(ss1), nb = neg2(n);
+            const f2 yr = rcp2_core(n, nb);
+            const f2 y = pk(tl0 ? lo(yr) : 0.f, tl1 ? hi(yr) : 0.f);
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                tvs0[c] = qdiv2(mul2(a1n, add2(gx0[c], gy0[c])), nb, y);   // compute.c:98: (a1 * -(gx+gy)) / n
+                tvr0[c] = qdiv2(mul2(a1s, gx0[c]), nb, y);                  // compute.c:100
+                N.tvb[c] = qdiv2(mul2(a1s, gy0[c]), nb, y);                 // compute.c:103
+            }
+        }
+        // ---- TGV quotients (compute.c:158-183), fast sequences ------------------------------
+        if (TGV) {
+            const f2 n = sqrt2_core(ss2), nb = neg2(n);
+            const f2 yr = rcp2_core(n, nb);
+            const f2 y = pk(gl0 ? lo(yr) : 0.f, gl1 ? hi(yr) : 0.f);
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                // compute.c:165: a2 * (-(2gxx + 2s + 2gyy) / n) == (-2 a2) * (((s + gxx) + gyy) / n): doubling
+                // commutes with every rounding involved (no overflow in this range)
+                const f2 sx = addm2(sym[c], gxx[c], one);
+                t2s0[c] = mul2(a2m2, qdiv2(add2(sx, gyy[c]), nb, y));
+                lr0[c] = mul2(a2s, qdiv2(sx, nb, y));                           // compute.c:167,170
+                N.ud[c] = mul2(a2s, qdiv2(addm2(sym[c], gyy[c], one), nb, y));        // compute.c:173,176
+                N.dg[c] = mul2(a2n, qdiv2(sym[c], nb, y));                      // compute.c:179,182: a2 * (-s / n)
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < NC; c++) t2s0[c] = lr0[c] = N.ud[c] = N.dg[c] = zero2;
+        }
+        // ---- outside the proven range (once in millions of rows): IEEE square root and division ----
+        if (__builtin_expect(!fast, false)) {
+            {
+                TvSlow<NC> io;
 #pragma unroll
                 for (int c = 0; c < NC; c++) {
-                    // compute.c:165: a2 * (-(2gxx + 2s + 2gyy) / n) == (-2 a2) * (((s + gxx) + gyy) / n): doubling
-                    // commutes with every rounding involved (no overflow in this range)
-                    const f2 sx = addm2(sym[c], gxx[c], one);
-                    t2s0[c] = mul2(a2m2, qdiv2(add2(sx, gyy[c]), nb, y));
-                    lr0[c] = mul2(a2s, qdiv2(sx, nb, y));                           // compute.c:167,170
-                    N.ud[c] = mul2(a2s, qdiv2(addm2(sym[c], gyy[c], one), nb, y));        // compute.c:173,176
-                    N.dg[c] = mul2(a2n, qdiv2(sym[c], nb, y));                      // compute.c:179,182: a2 * (-s / n)
+                    io.gx[c][0] = lo(gx0[c]); io.gx[c][1] = hi(gx0[c]);
+                    io.gy[c][0] = lo(gy0[c]); io.gy[c][1] = hi(gy0[c]);
                 }
-            } else {
+                tv_slow<NC>(&io, F.a1, src_in);
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    tvs0[c] = pk(settle(io.q[0][c][0], zero), settle(io.q[0][c][1], zero));
+                    tvr0[c] = pk(settle(io.q[1][c][0], zero), settle(io.q[1][c][1], zero));
+                    N.tvb[c] = pk(settle(io.q[2][c][0], zero), settle(io.q[2][c][1], zero));
+                }
+            }
+            if (TGV) {
                 TgvSlow<NC> io;
 #pragma unroll
                 for (int c = 0; c < NC; c++) {
@@ -340,40 +351,38 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient_packed(co
                     N.dg[c] = pk(settle(io.q[3][c][0], zero), settle(io.q[3][c][1], zero));
                 }
             }
-        } else {
-#pragma unroll
-            for (int c = 0; c < NC; c++) t2s0[c] = lr0[c] = N.ud[c] = N.dg[c] = zero2;
         }
 
         // ---- target row s-1: last two addends (TGV below-left, below), store, sum of squares ----
-        if (i >= yb + 2 && i <= ye + 1) {
-            f2 o[NC];
+        // Computed in every step; the rows that are not targets of this band (the two lead-in steps
+        // and the idle step of an odd band) only suppress the store and add zeros to the sums.
+        {
+            const bool st = is_target & (i >= yb + 2) & (i <= ye + 1);
+            const unsigned ro = (unsigned)max(s - 1, 0) * (unsigned)W;         // targets are inside the frame: pxc == px0
 #pragma unroll
             for (int c = 0; c < NC; c++) {
-                o[c] = P.og[c];
+                f2 o = P.og[c];
                 if (TGV) {
                     const float dgl = __shfl_up_sync(0xffffffffu, hi(N.dg[c]), 1);
-                    o[c] = addm2(N.ud[c], add2(o[c], shl_from_left(N.dg[c], dgl)), one);
+                    o = addm2(N.ud[c], add2(o, shl_from_left(N.dg[c], dgl)), one);
                 }
-            }
-            if (is_target) {
-                const unsigned ro = (unsigned)(s - 1) * (unsigned)W;           // targets are inside the frame: pxc == px0
-#pragma unroll
-                for (int c = 0; c < NC; c++) {
-                    float2 *dst = GPM != 0 ? reinterpret_cast<float2 *>(at(lp_g, ro + c * PS)) : reinterpret_cast<float2 *>(F.pl[c].g + (ro + (unsigned)px0));
-                    *dst = make_float2(lo(o[c]), hi(o[c]));
-                    const f2 sq = mul2(o[c], o[c]);
-                    acc[c] = __dadd_rn(acc[c], (double)lo(sq));       // compute.c:203
-                    acc[c] = __dadd_rn(acc[c], (double)hi(sq));
-                }
+                float2 *dst = GPM != 0 ? reinterpret_cast<float2 *>(at(lp_g, ro + c * PS)) : reinterpret_cast<float2 *>(F.pl[c].g + (ro + (unsigned)pxc));
+                if (st) *dst = make_float2(lo(o), hi(o));
+                const f2 sq = mul2(o, o);
+                acc[c] = __dadd_rn(acc[c], (double)(st ? lo(sq) : 0.f));      // compute.c:203; + 0.0 leaves the sum as it is
+                acc[c] = __dadd_rn(acc[c], (double)(st ? hi(sq) : 0.f));
             }
         }
 
-        // ---- target row s: addends 7..9 (TGV left, self, right of this row's quotients) ----------
+        // ---- target row s: addends 1..9 (DCT distance; TV above, left, self; TGV above, above-right,
+        // left, self, right) ---------------------------------------------------------------------
 #pragma unroll
         for (int c = 0; c < NC; c++) {
-            f2 o = oA[c];
+            const float tvr_l = __shfl_up_sync(0xffffffffu, hi(tvr0[c]), 1);
+            f2 o = add2(add2(add2(pterm[c], P.tvb[c]), shl_from_left(tvr0[c], tvr_l)), tvs0[c]);
             if (TGV) {
+                const float dg_r = __shfl_down_sync(0xffffffffu, lo(P.dg[c]), 1);
+                o = add2(addm2(P.ud[c], o, one), shr_from_right(P.dg[c], dg_r));
                 const float lr_l = __shfl_up_sync(0xffffffffu, hi(lr0[c]), 1);
                 const float lr_r = __shfl_down_sync(0xffffffffu, lo(lr0[c]), 1);
                 o = add2(addm2(t2s0[c], add2(o, shl_from_left(lr0[c], lr_l)), one), shr_from_right(lr0[c], lr_r));

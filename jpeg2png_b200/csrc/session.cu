@@ -401,6 +401,7 @@ static int create_impl(j2p_session *s, int device, const j2p_frame_desc *d, unsi
         maps_ok = encode_plane_map(&s->maps.m[c][0], s->x[c], F.W, F.H, box_rows) == 0 &&
                   encode_plane_map(&s->maps.m[c][1], s->xp[c], F.W, F.H, box_rows) == 0 &&
                   encode_plane_map(&s->maps.m[c][2], s->g[c], F.W, F.H, box_rows) == 0;
+        if (maps_ok && p11) maps_ok = encode_plane_map(&s->maps.m[c][3], s->gp[c], F.pl[c].cw, F.pl[c].ch, 8) == 0;
     }
     F.host_maps = maps_ok ? &s->maps : nullptr;
     F.buf_sel = 0;
