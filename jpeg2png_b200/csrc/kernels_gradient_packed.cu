@@ -52,8 +52,13 @@ __device__ __forceinline__ f2 shr_from_right(f2 v, float from_right) { return pk
 // GPM: how the DCT-distance term is addressed.  1 = every plane is full resolution and covers the
 // whole frame (4:4:4): gp has the frame's geometry, one 8-byte load per plane at the pixel offset.
 // 0 = generic (any sampling factors, grids smaller than the frame).
+#ifdef J2P_GRAD_MAXNREG      // A/B aid: an explicit register budget instead of the resident-CTA bound
+#define J2P_GRAD_BOUNDS __maxnreg__(J2P_GRAD_MAXNREG)
+#else
+#define J2P_GRAD_BOUNDS __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS)
+#endif
 template <int NC, bool TGV, int GPM>
-__global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient_packed(const __grid_constant__ FrameDev F, const float factor, const int band_rows) {
+__global__ void J2P_GRAD_BOUNDS k_gradient_packed(const __grid_constant__ FrameDev F, const float factor, const int band_rows) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int W = F.W, H = F.H;
     const int X0 = (blockIdx.x * GM_WARPS + wid) * GM_USE;   // first target column of this warp
@@ -460,18 +465,48 @@ __global__ void __launch_bounds__(GM_NT, J2P_GRAD_MIN_CTAS) k_gradient_packed(co
 // ------------------------------------------------------------------------------------------
 void grad_geometry(int W, int H, int slots, int *ctas_x, int *bands, int *band_rows);
 
+// CTAs of one kernel instantiation resident on the current device at once.  Per instantiation, not
+// per kernel family: the one-channel builds (separate mode, -s) need 72..86 registers and fit five
+// CTAs per SM where the three-channel joint build fits two — a band geometry sized for the wrong one
+// leaves most of the machine idle (measured: profiles/r02_ab_gradient_geometry.txt, the W5 rows).
+static int sm_count() {
+    static int sms[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int &n = sms[dev & 63];
+    if (n == 0 && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+        cudaGetLastError();
+        n = 148;
+    }
+    return n;
+}
+template <int NC, bool TGV, int GPM>
+static cudaError_t launch_instance(const FrameDev &F, float factor, cudaStream_t s) {
+    static const int per_sm = [] {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_gradient_packed<NC, TGV, GPM>, GM_NT, 0) != cudaSuccess) {
+            cudaGetLastError();
+            n = 0;
+        }
+        return n > 0 ? n : 1;
+    }();
+    int cx, bands, rows;
+    grad_geometry(F.W, F.t1 - F.t0, sm_count() * per_sm, &cx, &bands, &rows);
+    k_gradient_packed<NC, TGV, GPM><<<dim3(cx, bands), GM_NT, 0, s>>>(F, factor, rows);
+    return cudaGetLastError();
+}
 template <bool TGV, int GPM>
-static void launch_packed_nc(const FrameDev &F, float factor, dim3 grid, int rows, cudaStream_t s) {
+static cudaError_t launch_packed_nc(const FrameDev &F, float factor, cudaStream_t s) {
     switch (F.nc) {
-        case 1: k_gradient_packed<1, TGV, GPM><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
-        case 2: k_gradient_packed<2, TGV, GPM><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
-        default: k_gradient_packed<3, TGV, GPM><<<grid, GM_NT, 0, s>>>(F, factor, rows); break;
+        case 1: return launch_instance<1, TGV, GPM>(F, factor, s);
+        case 2: return launch_instance<2, TGV, GPM>(F, factor, s);
+        default: return launch_instance<3, TGV, GPM>(F, factor, s);
     }
 }
 
 int packed_gradient_occupancy() {
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gradient_packed<3, true, 0>, GM_NT, 0) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gradient_packed<3, true, 1>, GM_NT, 0) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
@@ -479,26 +514,15 @@ int packed_gradient_occupancy() {
 }
 
 cudaError_t launch_gradient_packed(const FrameDev &F, float factor, cudaStream_t s) {
-    int cx, bands, rows;
-    grad_geometry(F.W, F.t1 - F.t0, F.grad_slots, &cx, &bands, &rows);
-    const dim3 grid(cx, bands);
     const int owned = F.t1 - F.t0;
     bool full = true;      // every plane at full resolution over the whole (local) frame: gp has the frame's geometry
     for (int c = 0; c < F.nc; c++) full = full && F.pl[c].sw == 1 && F.pl[c].sh == 1 && F.pl[c].cw == F.W && F.pl[c].ch >= owned;
     // 4:2:0 with aligned grids: luma full width (its last rows may be missing: 1080p), both chroma planes exactly half
     bool c420 = F.nc == 3 && F.pl[0].sw == 1 && F.pl[0].sh == 1 && F.pl[0].cw == F.W;
     for (int c = 1; c < 3 && c420; c++) c420 = F.pl[c].sw == 2 && F.pl[c].sh == 2 && 2 * F.pl[c].cw == F.W && F.pl[c].ch == F.pl[1].ch;
-    if (full) {
-        if (F.use_tgv) launch_packed_nc<true, 1>(F, factor, grid, rows, s);
-        else launch_packed_nc<false, 1>(F, factor, grid, rows, s);
-    } else if (c420) {
-        if (F.use_tgv) k_gradient_packed<3, true, 2><<<grid, GM_NT, 0, s>>>(F, factor, rows);
-        else k_gradient_packed<3, false, 2><<<grid, GM_NT, 0, s>>>(F, factor, rows);
-    } else {
-        if (F.use_tgv) launch_packed_nc<true, 0>(F, factor, grid, rows, s);
-        else launch_packed_nc<false, 0>(F, factor, grid, rows, s);
-    }
-    return cudaGetLastError();
+    if (full) return F.use_tgv ? launch_packed_nc<true, 1>(F, factor, s) : launch_packed_nc<false, 1>(F, factor, s);
+    if (c420) return F.use_tgv ? launch_instance<3, true, 2>(F, factor, s) : launch_instance<3, false, 2>(F, factor, s);
+    return F.use_tgv ? launch_packed_nc<true, 0>(F, factor, s) : launch_packed_nc<false, 0>(F, factor, s);
 }
 
 }  // namespace j2p

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(PT_NT, J2P_TILE_MIN_CTAS) k_project_tile(const
     const PlaneDev &P = F.pl[c];
     const int W = F.W;
     const int bw = P.cw >> 3;
-    const int bx0 = blockIdx.x * 32, by = blockIdx.y;            // the grid covers real blocks only
+    const int bx0 = blockIdx.x * 32, by = strip_row_order(F.sync, blockIdx.y, gridDim.y);   // the grid covers real blocks only
     const int nbx = min(32, bw - bx0);                           // blocks of this tile that exist
     const int valid_c4 = nbx * 2;
     const size_t row0 = (size_t)(by * 8) * W + (size_t)bx0 * 8;  // first pixel of the tile

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(P22_NT, 3) k_project_tile22(const __grid_const
     const PlaneDev &P = F.pl[c];
     const int W = F.W;
     const int bw = P.cw >> 3;
-    const int bx0 = blockIdx.x * P22_NB, by = blockIdx.y;            // the grid covers real blocks only
+    const int bx0 = blockIdx.x * P22_NB, by = strip_row_order(F.sync, blockIdx.y, gridDim.y);   // the grid covers real blocks only
     const int nbx = min(P22_NB, bw - bx0);
     const int valid_c4 = nbx * 4, valid_g4 = nbx * 2;
     const size_t row0 = (size_t)(by * 16) * W + (size_t)bx0 * 16;    // first frame pixel of the tile

@@ -30,20 +30,23 @@ struct Stepper {
 
 // The same on two adjacent pixels at once (packed fp32, numerics.cuh): half the issue slots.
 //   y - step * q  ==  y + (-step) * q  bit for bit; the sum with the product goes through addm2().
+// Branch-free: when the norm is zero (compute.c:211 skips the step) the constants are replaced so that
+// the same instruction sequence leaves y untouched, bit for bit.  Then every g is +0 (a sum of squares
+// is zero only if every term is, and the gradient kernel never produces -0: its first addend is
+// fma(gp, mask, +0)), the quotient sequence on (g = +0, -b = -1, 1/b = 0) yields +0, the product with
+// -0.0f is -0, and y + (-0) == y for every y including -0.
 struct Stepper2 {
     f2 fac, nstep, nnorm, rn, one;
-    bool stepping;
     __device__ __forceinline__ void init(const Stepper &s, float one_) {
-        fac = splat(s.factor); nstep = splat(-s.step); nnorm = splat(-s.norm); rn = splat(s.rn); one = splat(one_);
-        stepping = s.stepping;
+        fac = splat(s.factor); one = splat(one_);
+        nstep = splat(s.stepping ? -s.step : -0.0f);
+        nnorm = splat(s.stepping ? -s.norm : -1.0f);
+        rn = splat(s.stepping ? s.rn : 0.0f);
     }
     __device__ __forceinline__ f2 fast(f2 x, f2 xp, f2 g, unsigned &key) const {
-        f2 y = addm2(mul2(fac, sub2(x, xp)), x, one);
-        if (stepping) {
-            key = min(key, min(qdiv_key(lo(g)), qdiv_key(hi(g))));
-            y = addm2(mul2(nstep, qdiv2(g, nnorm, rn)), y, one);
-        }
-        return y;
+        const f2 y = addm2(mul2(fac, sub2(x, xp)), x, one);
+        key = min(key, min(qdiv_key(lo(g)), qdiv_key(hi(g))));
+        return addm2(mul2(nstep, qdiv2(g, nnorm, rn)), y, one);
     }
 };
 

@@ -115,6 +115,16 @@ __device__ __forceinline__ void strip_norm(const FrameDev &F, int c, float *out,
     }
 }
 
+// Projection kernels of a strip session walk their block rows in the order first, last, then the
+// interior: the rows the neighbours wait for are projected, stored across NVLink and flagged while
+// the interior is still being worked on, so the neighbours' next k_gradient finds its halo rows in
+// place instead of waiting for the tail of this kernel (the two exchanges of an iteration then share
+// one rank-to-rank synchronisation point, the sums, instead of two).
+__device__ __forceinline__ int strip_row_order(const StripSync &S, int y, int rows) {
+    if (S.nranks <= 1 || rows < 3) return y;
+    return y == 0 ? 0 : (y == 1 ? rows - 1 : y - 1);
+}
+
 // Projection kernels with fused halo delivery: a CTA that has stored its share of the strip's
 // first (side 0) / last (side 1) two rows into the neighbour calls this with all its threads after
 // those stores.  The last such CTA of the iteration raises the neighbour's flag.

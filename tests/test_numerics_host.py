@@ -45,26 +45,29 @@ def test_packed_products_are_not_contracted(tmp_path):
     if not (os.path.exists(nvcc) and os.path.exists(cuobjdump)):
         import pytest
         pytest.skip('CUDA toolkit not installed')
-    src = os.path.join(ROOT, 'jpeg2png_b200', 'csrc', 'kernels_gradient_packed.cu')
     flags = ['-O3', '-std=c++17', '-fmad=false', '-prec-div=true', '-prec-sqrt=true', '-ftz=false']
-    ptx, cubin = str(tmp_path / 'k.ptx'), str(tmp_path / 'k.cubin')
-    subprocess.run([nvcc, '-gencode', 'arch=compute_100a,code=compute_100a', *flags, '-ptx', '-o', ptx, src], check=True, capture_output=True)
-    subprocess.run([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', *flags, '-cubin', '-o', cubin, src], check=True, capture_output=True)
-    want = {}
-    for entry in re.split(r'\n\.visible \.entry ', open(ptx).read())[1:]:
-        c = collections.Counter(re.findall(r'\b(fma|mul|add|sub)\.rn\.f32x2\b', entry))
-        want[entry.split('(')[0].strip()] = (c['fma'], c['mul'], c['add'] + c['sub'])
-    sass = subprocess.run([cuobjdump, '-sass', cubin], check=True, capture_output=True, text=True).stdout
-    seen = 0
-    for fun in re.split(r'\n\s+Function : ', sass)[1:]:
-        name = fun.split('\n')[0].strip()
-        if name not in want:
-            continue
-        c = collections.Counter(re.findall(r'\b(FFMA2|FMUL2|FADD2)\b', fun))
-        assert (c['FFMA2'], c['FMUL2'], c['FADD2']) == want[name], f'{name}: SASS {dict(c)} vs PTX fma/mul/add+sub {want[name]}'
-        assert want[name][0] > 30, 'the kernel no longer uses packed fp32?'
-        seen += 1
-    assert seen >= 12
+    # (source, packed FMAs a kernel must at least have, kernels expected): the gradient kernel and the
+    # projection kernels whose stepper / clamp sections run on packed fp32
+    for base, min_fma, min_kernels in (('kernels_gradient_packed', 30, 12), ('kernels_project_tma', 10, 2)):
+        src = os.path.join(ROOT, 'jpeg2png_b200', 'csrc', base + '.cu')
+        ptx, cubin = str(tmp_path / (base + '.ptx')), str(tmp_path / (base + '.cubin'))
+        subprocess.run([nvcc, '-gencode', 'arch=compute_100a,code=compute_100a', *flags, '-ptx', '-o', ptx, src], check=True, capture_output=True)
+        subprocess.run([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', *flags, '-cubin', '-o', cubin, src], check=True, capture_output=True)
+        want = {}
+        for entry in re.split(r'\n\.visible \.entry ', open(ptx).read())[1:]:
+            c = collections.Counter(re.findall(r'\b(fma|mul|add|sub)\.rn\.f32x2\b', entry))
+            want[entry.split('(')[0].strip()] = (c['fma'], c['mul'], c['add'] + c['sub'])
+        sass = subprocess.run([cuobjdump, '-sass', cubin], check=True, capture_output=True, text=True).stdout
+        seen = 0
+        for fun in re.split(r'\n\s+Function : ', sass)[1:]:
+            name = fun.split('\n')[0].strip()
+            if name not in want or want[name] == (0, 0, 0):
+                continue
+            c = collections.Counter(re.findall(r'\b(FFMA2|FMUL2|FADD2)\b', fun))
+            assert (c['FFMA2'], c['FMUL2'], c['FADD2']) == want[name], f'{name}: SASS {dict(c)} vs PTX fma/mul/add+sub {want[name]}'
+            assert want[name][0] > min_fma, f'{name} no longer uses packed fp32?'
+            seen += 1
+        assert seen >= min_kernels, base
 
 
 def test_small_int_to_float_trick():

@@ -9,10 +9,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from jpeg2png_b200 import abi, synth  # noqa: E402
 
 w, h, q, ss, iters = 3840, 2160, 50, '4:4:4', 12
+lib_path = None
+if len(sys.argv) > 2 and sys.argv[1] == '--lib':      # an A/B build (tools/build_variant.sh)
+    lib_path = sys.argv[2]
+    del sys.argv[1:3]
 if len(sys.argv) > 1:
     w, h, q, ss, iters = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), sys.argv[4], int(sys.argv[5])
 img = synth.synth_coefs(w, h, q, ss, 1237)
-lib = abi.load_product()
+lib = abi.declare_product(C.CDLL(lib_path, mode=C.RTLD_LOCAL)) if lib_path else abi.load_product()
 d = abi.FrameDesc()
 d.nchannel = 3
 for c, p in enumerate(img.planes):
