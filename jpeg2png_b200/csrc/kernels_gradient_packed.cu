@@ -296,11 +296,12 @@ __global__ void J2P_GRAD_BOUNDS k_gradient_packed(const __grid_constant__ FrameD
             const f2 n = sqrt2_core(ss1), nb = neg2(n);
             const f2 yr = rcp2_core(n, nb);
             const f2 y = pk(tl0 ? lo(yr) : 0.f, tl1 ? hi(yr) : 0.f);
+            const f2 yl = rcp2_low(nb, y);                                  // two-term reciprocal: four operations per quotient (numerics.cuh)
 #pragma unroll
             for (int c = 0; c < NC; c++) {
-                tvs0[c] = qdiv2(mul2(a1n, add2(gx0[c], gy0[c])), nb, y);   // compute.c:98: (a1 * -(gx+gy)) / n
-                tvr0[c] = qdiv2(mul2(a1s, gx0[c]), nb, y);                  // compute.c:100
-                N.tvb[c] = qdiv2(mul2(a1s, gy0[c]), nb, y);                 // compute.c:103
+                tvs0[c] = qdiv2x(mul2(a1n, add2(gx0[c], gy0[c])), nb, y, yl);   // compute.c:98: (a1 * -(gx+gy)) / n
+                tvr0[c] = qdiv2x(mul2(a1s, gx0[c]), nb, y, yl);                  // compute.c:100
+                N.tvb[c] = qdiv2x(mul2(a1s, gy0[c]), nb, y, yl);                 // compute.c:103
             }
         }
         // ---- TGV quotients (compute.c:158-183), fast sequences ------------------------------
@@ -308,15 +309,16 @@ __global__ void J2P_GRAD_BOUNDS k_gradient_packed(const __grid_constant__ FrameD
             const f2 n = sqrt2_core(ss2), nb = neg2(n);
             const f2 yr = rcp2_core(n, nb);
             const f2 y = pk(gl0 ? lo(yr) : 0.f, gl1 ? hi(yr) : 0.f);
+            const f2 yl = rcp2_low(nb, y);
 #pragma unroll
             for (int c = 0; c < NC; c++) {
                 // compute.c:165: a2 * (-(2gxx + 2s + 2gyy) / n) == (-2 a2) * (((s + gxx) + gyy) / n): doubling
                 // commutes with every rounding involved (no overflow in this range)
                 const f2 sx = addm2(sym[c], gxx[c], one);
-                t2s0[c] = mul2(a2m2, qdiv2(add2(sx, gyy[c]), nb, y));
-                lr0[c] = mul2(a2s, qdiv2(sx, nb, y));                           // compute.c:167,170
-                N.ud[c] = mul2(a2s, qdiv2(addm2(sym[c], gyy[c], one), nb, y));        // compute.c:173,176
-                N.dg[c] = mul2(a2n, qdiv2(sym[c], nb, y));                      // compute.c:179,182: a2 * (-s / n)
+                t2s0[c] = mul2(a2m2, qdiv2x(add2(sx, gyy[c]), nb, y, yl));
+                lr0[c] = mul2(a2s, qdiv2x(sx, nb, y, yl));                           // compute.c:167,170
+                N.ud[c] = mul2(a2s, qdiv2x(addm2(sym[c], gyy[c], one), nb, y, yl));        // compute.c:173,176
+                N.dg[c] = mul2(a2n, qdiv2x(sym[c], nb, y, yl));                      // compute.c:179,182: a2 * (-s / n)
             }
         } else {
 #pragma unroll
