@@ -423,14 +423,20 @@ __global__ void J2P_GRAD_BOUNDS k_gradient_packed(const __grid_constant__ FrameD
     }
     __syncthreads();
     const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x, ncta = gridDim.x * gridDim.y;
-    if (tid < NC) {
-        double sum = 0.;
-        for (int k = 0; k < GM_WARPS; k++) sum = __dadd_rn(sum, red[tid][k]);
-        F.partials[(size_t)tid * F.grad_ctas + cta] = sum;
+    // One thread publishes the CTA's partial sums and takes the ticket with RELEASE semantics: only
+    // these few stores have to be visible to the CTA that folds them.  (A __threadfence() by every
+    // thread made each CTA wait for all of its gradient stores to drain before it could retire.)
+    if (tid == 0) {
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            double sum = 0.;
+            for (int k = 0; k < GM_WARPS; k++) sum = __dadd_rn(sum, red[c][k]);
+            F.partials[(size_t)c * F.grad_ctas + cta] = sum;
+        }
+        unsigned t;
+        asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(F.counter) : "memory");
+        ticket = t;
     }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) ticket = atomicAdd(F.counter, 1u);
     __syncthreads();
     if (ticket == ncta - 1) {
         __threadfence();
