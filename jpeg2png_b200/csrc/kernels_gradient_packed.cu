@@ -30,6 +30,7 @@
 #include "gradient_common.cuh"
 #include "kernels.cuh"
 #include "numerics.cuh"
+#include "pdl.cuh"
 #include "project_common.cuh"
 #include "strip_sync.cuh"
 
@@ -74,6 +75,11 @@ __global__ void J2P_GRAD_BOUNDS k_gradient_packed(const __grid_constant__ FrameD
     const f2 one = splat(F.one);                             // see addm2(): sums with a product go through fma(m, one, b)
     const unsigned zero = (unsigned)band_rows >> 31;         // see settle()
 
+    // Everything the kernel reads was written by the projection before it (x_k, gp, the halo rows):
+    // nothing but index arithmetic runs ahead of the wait.  The dependents (the projection of this
+    // iteration) may take their seats once this kernel is really running.
+    pdl_wait();
+    pdl_launch_dependents();
     // strip sessions: the halo rows of x_k arrive from the neighbours' projection (strip_sync.cuh)
     strip_wait_halo(F.sync, blockIdx.y == 0, blockIdx.y == gridDim.y - 1);
 
@@ -500,8 +506,7 @@ static cudaError_t launch_instance(const FrameDev &F, float factor, cudaStream_t
     }();
     int cx, bands, rows;
     grad_geometry(F.W, F.t1 - F.t0, sm_count() * per_sm, &cx, &bands, &rows);
-    k_gradient_packed<NC, TGV, GPM><<<dim3(cx, bands), GM_NT, 0, s>>>(F, factor, rows);
-    return cudaGetLastError();
+    return launch_chain(k_gradient_packed<NC, TGV, GPM>, dim3(cx, bands), dim3(GM_NT), 0, s, F, factor, rows);
 }
 template <bool TGV, int GPM>
 static cudaError_t launch_packed_nc(const FrameDev &F, float factor, cudaStream_t s) {

@@ -17,6 +17,7 @@
 
 #include "kernels.cuh"
 #include "numerics.cuh"
+#include "pdl.cuh"
 #include "project_common.cuh"
 #include "strip_sync.cuh"
 
@@ -48,6 +49,10 @@ __global__ void __launch_bounds__(PT_NT, J2P_TILE_MIN_CTAS) k_project_tile(const
     const size_t row0 = (size_t)(by * 8) * W + (size_t)bx0 * 8;  // first pixel of the tile
 
     // ---- coalesced, swizzled copy-in ------------------------------------------------------------
+    // x_k and x_{k-1} are not written by the gradient kernel this launch depends on (pdl.cuh): their
+    // tiles are requested BEFORE the wait, while that kernel drains.  Everything else follows the wait
+    // at once: in all but the first wave of CTAs it returns immediately, and the g tile must not queue
+    // behind the table loads (20 waves of short-lived CTAs pay their prologue latency in the open).
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         const int e = tid + PT_NT * i, row = e >> 6, c4 = e & 63;
@@ -55,8 +60,14 @@ __global__ void __launch_bounds__(PT_NT, J2P_TILE_MIN_CTAS) k_project_tile(const
             const size_t gi = row0 + (size_t)row * W + (size_t)c4 * 4;
             cp_async16(&sx[row][c4 ^ row], P.x + gi);
             cp_async16(&sp[row][c4 ^ row], P.xp + gi);
-            cp_async16(&sg[row][c4 ^ row], P.g + gi);
         }
+    }
+    pdl_wait();                                                  // the gradient and its norm are complete and visible
+    pdl_launch_dependents();
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const int e = tid + PT_NT * i, row = e >> 6, c4 = e & 63;
+        if (c4 < valid_c4) cp_async16(&sg[row][c4 ^ row], P.g + row0 + (size_t)row * W + (size_t)c4 * 4);
     }
     cp_async_commit();
     const int b = tid >> 3, j = tid & 7;
@@ -67,9 +78,8 @@ __global__ void __launch_bounds__(PT_NT, J2P_TILE_MIN_CTAS) k_project_tile(const
         sq[0][tid] = F.q[c][tid];
         sq[1][tid] = F.qq[c][tid];
         sq[2][tid] = F.rqq[c][tid];
-    } else if (tid < 96) {
-        strip_norm(F, c, snorm, tid - 64);                       // whole frame: what k_gradient left; strips: fold of every rank's sums
     }
+    if (tid >= 64 && tid < 96) strip_norm(F, c, snorm, tid - 64);    // whole frame: what k_gradient left; strips: fold of every rank's sums
     cp_async_wait<0>();
     __syncthreads();
 
@@ -256,9 +266,7 @@ cudaError_t launch_project_tile(const FrameDev &F, int c, int count, float facto
     const dim3 grid((bw + 31) / 32, bh, count);
     cudaError_t e = cudaSuccess;
     if (!uncovered_only) {
-        if (P.resample) k_project_tile<true><<<grid, PT_NT, 0, s>>>(F, c, factor);
-        else k_project_tile<false><<<grid, PT_NT, 0, s>>>(F, c, factor);
-        e = cudaGetLastError();
+        e = P.resample ? launch_chain(k_project_tile<true>, grid, dim3(PT_NT), 0, s, F, c, factor) : launch_chain(k_project_tile<false>, grid, dim3(PT_NT), 0, s, F, c, factor);
         *nlaunch += 1;
     }
     for (int k = c; k < c + count && e == cudaSuccess; k++)

@@ -18,6 +18,7 @@
 
 #include "kernels.cuh"
 #include "numerics.cuh"
+#include "pdl.cuh"
 #include "project_common.cuh"
 #include "strip_sync.cuh"
 
@@ -53,6 +54,9 @@ __global__ void __launch_bounds__(P22_NT, 3) k_project_tile22(const __grid_const
     const size_t row0 = (size_t)(by * 16) * W + (size_t)bx0 * 16;    // first frame pixel of the tile
 
     // ---- coalesced, swizzled copy-in: 16 rows x 64 pieces per array, 8 pieces per thread ----------
+    // x_k and x_{k-1} of these planes are not written by the kernels this launch may overlap (the
+    // gradient kernel, the luma projection; pdl.cuh): their tiles are requested
+    // BEFORE the wait; the g tile follows it at once (kernels_project_tile.cu).
 #pragma unroll
     for (int i = 0; i < 16 * P22_C4 / P22_NT; i++) {
         const int e = tid + P22_NT * i, row = e / P22_C4, c4 = e % P22_C4;
@@ -61,8 +65,14 @@ __global__ void __launch_bounds__(P22_NT, 3) k_project_tile22(const __grid_const
             const int pc = row * P22_C4 + (c4 ^ ((row >> 1) & 7));
             cp_async16(&sx[pc], P.x + gi);
             cp_async16(&sp[pc], P.xp + gi);
-            cp_async16(&sg[pc], P.g + gi);
         }
+    }
+    pdl_wait();                                                      // the gradient and its norm are complete and visible
+    pdl_launch_dependents();
+#pragma unroll
+    for (int i = 0; i < 16 * P22_C4 / P22_NT; i++) {
+        const int e = tid + P22_NT * i, row = e / P22_C4, c4 = e % P22_C4;
+        if (c4 < valid_c4) cp_async16(&sg[row * P22_C4 + (c4 ^ ((row >> 1) & 7))], P.g + row0 + (size_t)row * W + (size_t)c4 * 4);
     }
     cp_async_commit();
     const int b = tid >> 3, j = tid & 7;
@@ -73,9 +83,8 @@ __global__ void __launch_bounds__(P22_NT, 3) k_project_tile22(const __grid_const
         sq[tid] = F.q[c][tid];
         sq[64 + tid] = F.qq[c][tid];
         sq[128 + tid] = F.rqq[c][tid];
-    } else if (tid < 96) {
-        strip_norm(F, c, snorm, tid - 64);                           // whole frame: what k_gradient left; strips: fold of every rank's sums
     }
+    if (tid >= 64 && tid < 96) strip_norm(F, c, snorm, tid - 64);    // whole frame: what k_gradient left; strips: fold of every rank's sums
     cp_async_wait<0>();
     __syncthreads();
 
@@ -273,8 +282,7 @@ cudaError_t launch_project_tile22(const FrameDev &F, int c, int count, float fac
     const PlaneDev &P = F.pl[c];
     const int bw = P.cw >> 3, bh = P.ch >> 3;
     const dim3 grid((bw + P22_NB - 1) / P22_NB, bh, count);
-    k_project_tile22<<<grid, P22_NT, P22_SMEM, s>>>(F, c, factor);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_chain(k_project_tile22, grid, dim3(P22_NT), P22_SMEM, s, F, c, factor);
     *nlaunch += 1;
     for (int k = c; k < c + count && e == cudaSuccess; k++) {
         const PlaneDev &Q = F.pl[k];

@@ -68,6 +68,11 @@ static int fail(int code, const char *fmt, ...) {
     } while (0)
 
 constexpr int kEventRing = 32;
+// An event is recorded after every kEventStride-th iteration only: an event record between two kernels
+// keeps the second from being launched as a programmatic dependent of the first (pdl.cuh).  Waiting
+// for iteration i means waiting for the first recorded iteration >= i (stream order), or for the
+// stream when none has been recorded yet.
+constexpr unsigned kEventStride = 4;
 
 // ---- device memory: a process-wide cache of device blocks keyed by (device, exact size).  A
 // session takes its ~25 blocks from it and gives them back when it is destroyed (its stream is
@@ -459,6 +464,7 @@ static int reset_impl(j2p_session *s) {
     }
     s->t = 1.f;
     s->next_iter = 0;
+    for (int i = 0; i < kEventRing; i++) s->ev_iter[i] = -1;            // events of an earlier solve say nothing about this one
     s->next_log_iter = 0;
     s->log_host_iter = -1;
     CK(cudaMemsetAsync(F.logsums, 0, sizeof(double) * 8, s->stream));    // iteration 0: DCT distance is exactly 0
@@ -700,9 +706,11 @@ extern "C" int j2p_session_iterate(j2p_session *s, unsigned first, unsigned n) {
     for (unsigned i = first; i < first + n; i++) {
         rc = one_iteration(s, nullptr, nullptr, nullptr);
         if (rc != J2P_OK) return rc;
-        const int slot = (int)(i % kEventRing);
-        CK(cudaEventRecord(s->ev[slot], s->stream));
-        s->ev_iter[slot] = (long long)i;
+        if (i % kEventStride == kEventStride - 1) {
+            const int slot = (int)((i / kEventStride) % kEventRing);
+            CK(cudaEventRecord(s->ev[slot], s->stream));
+            s->ev_iter[slot] = (long long)i;
+        }
     }
     s->next_iter = first + n;
     return J2P_OK;
@@ -736,17 +744,17 @@ extern "C" int j2p_session_profile(j2p_session *s, unsigned n, float *ms_gradien
 extern "C" int j2p_session_wait_iteration(j2p_session *s, unsigned iter) {
     if (!s) return fail(J2P_ERR_ARG, "null session");
     CK(cudaSetDevice(s->device));
-    const int slot = (int)(iter % kEventRing);
-    if (s->ev_iter[slot] == (long long)iter) {
+    if (iter >= s->next_iter) return fail(J2P_ERR_ARG, "iteration %u has not been queued", iter);
+    // the first iteration at or after `iter` that carries an event
+    const unsigned marked = iter | (kEventStride - 1);
+    const int slot = (int)((marked / kEventStride) % kEventRing);
+    if (marked < s->next_iter && s->ev_iter[slot] >= (long long)marked) {
+        // the slot holds `marked` itself, or (recycled after kEventRing * kEventStride more iterations) a later
+        // iteration: events mark where an iteration was QUEUED, and stream order makes the older one complete
+        // once the later one is
         CK(cudaEventSynchronize(s->ev[slot]));
-    } else if (iter >= s->next_iter) {
-        return fail(J2P_ERR_ARG, "iteration %u has not been queued", iter);
     } else {
-        // Its event slot has been recycled by a later iteration (more than kEventRing iterations were
-        // queued since).  Events mark where an iteration was QUEUED, so that alone says nothing about
-        // completion: wait for the iteration that took the slot — stream order makes the older one
-        // complete by then.
-        CK(cudaEventSynchronize(s->ev[slot]));
+        CK(cudaStreamSynchronize(s->stream));     // nothing recorded at or after it yet: the tail of a solve
     }
     return J2P_OK;
 }

@@ -39,7 +39,17 @@ for path in libs:
     mg, mp = C.c_float(), C.c_float()
     lib.j2p_session_profile(s, 10, C.byref(mg), C.byref(mp))
     lib.j2p_session_profile(s, 40, C.byref(mg), C.byref(mp))
+    # whole solves queued back to back (what bench.py's `value` times): wall clock around 3 x 100 iterations
+    import time
+    lib.j2p_session_iterate(s, 0, 100)
+    lib.j2p_session_sync(s)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        lib.j2p_session_iterate(s, 0, 100)
+    lib.j2p_session_sync(s)
+    solve_us = (time.perf_counter() - t0) / 300 * 1e6
+    lib.j2p_session_profile(s, 40, C.byref(mg), C.byref(mp))       # leaves the session after 40 iterations, as before
     out = np.empty((img.frame_h, img.frame_w), np.float32)
     lib.j2p_session_download(s, 0, out.ctypes.data)
-    print(f'{os.path.basename(path):40s} gradient {mg.value*1e3:8.1f} us  project {mp.value*1e3:8.1f} us  sum {(mg.value+mp.value)*1e3:8.1f} us  checksum {float(np.float64(out).sum()):.6f}')
+    print(f'{os.path.basename(path):40s} gradient {mg.value*1e3:8.1f} us  project {mp.value*1e3:8.1f} us  sum {(mg.value+mp.value)*1e3:8.1f} us  in-solve {solve_us:8.1f} us/iteration  checksum {float(np.float64(out).sum()):.6f}')
     lib.j2p_session_destroy(s)
