@@ -104,6 +104,8 @@ static void usage(void) {
         exit(EXIT_FAILURE);
 }
 
+static double now_ms(void);
+
 /* ---- one file (reference decode_file, jpeg2png.c:120-172) ------------------------------------ */
 struct job {
         unsigned iterations[3];
@@ -127,13 +129,18 @@ static void solve(const struct j2p_jpeg *jpeg, const unsigned *chan, unsigned nc
                 d.plane_w[k] = c->w; d.plane_h[k] = c->h; d.w_samp[k] = c->w_samp; d.h_samp[k] = c->h_samp;
                 d.pweight[k] = job->pweights[chan[k]];
         }
+        const char *tr = getenv("J2P_TRACE");
+        const int trace = tr && *tr == '1';
+        double t0 = trace ? now_ms() : 0, t1;
         j2p_session *s = NULL;
         if (j2p_session_create(&s, device, &d) != J2P_OK) die("%s", j2p_last_error());
+        if (trace) { t1 = now_ms(); fprintf(stderr, "j2p trace:   %s: session create %.1f ms", infile, t1 - t0); t0 = t1; }
         if (csv_log && j2p_session_set_logging(s, 1) != J2P_OK) die("%s", j2p_last_error());
         for (unsigned k = 0; k < nchan; k++) {
                 const struct coef *c = &jpeg->coefs[chan[k]];
                 if (j2p_session_upload(s, k, c->data, c->quant_table, NULL) != J2P_OK) die("%s", j2p_last_error());   /* decode on the device */
         }
+        if (trace) { t1 = now_ms(); fprintf(stderr, ", upload %.1f ms", t1 - t0); t0 = t1; }
         unsigned reported = 0;
         for (unsigned i = 0; i < iterations; i++) {
                 if (j2p_session_iterate(s, i, 1) != J2P_OK) die("%s", j2p_last_error());
@@ -147,11 +154,14 @@ static void solve(const struct j2p_jpeg *jpeg, const unsigned *chan, unsigned nc
         if (pb) for (; reported < iterations; reported++) { j2p_session_wait_iteration(s, reported); pb_add(pb, 1); }
         *out_w = j2p_session_width(s);
         *out_h = j2p_session_height(s);
+        if (trace) { t1 = now_ms(); fprintf(stderr, ", %u iterations queued %.1f ms", iterations, t1 - t0); t0 = t1; }
         if (scanlines) {
                 *scanlines = malloc((size_t)jpeg->h * ((size_t)jpeg->w * 3 * (job->png_bits / 8) + 1));
                 if (!*scanlines) die("allocation error");
                 if (j2p_session_download_scanlines(s, jpeg->w, jpeg->h, job->png_bits, *scanlines) != J2P_OK) die("%s", j2p_last_error());
+                if (trace) { t1 = now_ms(); fprintf(stderr, ", drain + scanlines %.1f ms", t1 - t0); t0 = t1; }
                 j2p_session_destroy(s);
+                if (trace) fprintf(stderr, ", destroy %.1f ms\n", now_ms() - t0);
                 return;
         }
         for (unsigned k = 0; k < nchan; k++) {

@@ -14,7 +14,10 @@ namespace j2p {
 #define J2P_GM_WARPS 4
 #endif
 constexpr int GM_WARPS = J2P_GM_WARPS, GM_NT = GM_WARPS * 32, GM_USE = 60;
-constexpr int GM_DEPTH = 4;      // packed kernel: rows in flight per warp (cp.async ring in shared memory); a power of two
+#ifndef J2P_GM_DEPTH
+#define J2P_GM_DEPTH 4
+#endif
+constexpr int GM_DEPTH = J2P_GM_DEPTH;      // packed kernel: rows in flight per warp (cp.async ring in shared memory); a power of two
 #ifndef J2P_GRAD_MIN_CTAS
 #define J2P_GRAD_MIN_CTAS 2     // resident CTAs per SM the register allocation is bounded for.  Measured on the one-block row step at 4K
                                 // (profiles/r02_ab_gradient_geometry.txt): 2 CTAs (194 registers, 8 warps/SM) 117.6 us, 3 CTAs (162 registers,

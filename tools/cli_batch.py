@@ -31,4 +31,4 @@ with tempfile.TemporaryDirectory() as d:
         print(f'cli batch: {n} x 1920x1080 Q75 4:2:0, -i 100{" -t " + threads if threads else ""}: {dt:.2f} s  '
               f'{n / dt:.1f} files/s  {n * 1920 * 1080 * 100 / dt / 1e6:.0f} Mpix-it/s (JPEG read + solve + PNG write)', flush=True)
         if rep == 1:
-            print('\n'.join(l for l in r.stderr.splitlines() if 'read+parse' in l)[:4000], flush=True)
+            print('\n'.join(l for l in r.stderr.splitlines() if "read+parse" in l or "session create" in l)[:9000], flush=True)
