@@ -490,7 +490,26 @@ static double now_ms() {
 // ---- staging ring: four pinned 8 MB buffers per session, each with the event of the last DMA that
 // used it.  A transfer of any size walks the ring; nothing drains between the arrays of an upload,
 // so the host copy of one array overlaps the DMA of the previous one.
-static int stage_slot(j2p_session *s, int *slot_out) {
+// reuse_idle (uploads): take a buffer whose last DMA has already completed before touching another
+// one.  Pinning is the expensive part of a short solve — sixteen command-line threads pinning four
+// 8 MB buffers each spent 1.6 s of a 3 s batch inside cudaHostAlloc (profiles/r02_notes.md) — and
+// the three small uploads of a 1080p file never have two DMAs in flight.  Downloads keep the strict
+// rotation: there a buffer is free only once the HOST has copied it out, which the events do not say.
+static int stage_slot(j2p_session *s, int *slot_out, bool reuse_idle = false) {
+    if (reuse_idle) {
+        for (int i = 0; i < kStageSlots; i++) {
+            const int k = (int)((s->stage_next + i) % kStageSlots);
+            if (!s->stage[k]) continue;
+            const cudaError_t q = cudaEventQuery(s->stage_ev[k]);
+            if (q == cudaSuccess) {
+                s->stage_next = (unsigned)k + 1;
+                *slot_out = k;
+                return J2P_OK;
+            }
+            if (q != cudaErrorNotReady) return fail(J2P_ERR_CUDA, "%s", cudaGetErrorString(q));
+            cudaGetLastError();
+        }
+    }
     const int k = (int)(s->stage_next++ % kStageSlots);
     if (!s->stage[k]) {
         s->stage[k] = g_pinned.get();
@@ -511,7 +530,7 @@ static int staged_h2d(j2p_session *s, void *dst, const void *src, size_t bytes) 
         const size_t n = bytes - off < kStageChunk ? bytes - off : kStageChunk;
         int k;
         const double t0 = now_ms();
-        const int rc = stage_slot(s, &k);
+        const int rc = stage_slot(s, &k, true);
         if (rc != J2P_OK) return rc;
         const double t1 = now_ms();
         par_memcpy(s->stage[k], (const char *)src + off, n);
@@ -530,6 +549,13 @@ static int staged_h2d(j2p_session *s, void *dst, const void *src, size_t bytes) 
 static int staged_d2h(j2p_session *s, void *dst, const void *src, size_t bytes) {
     const size_t nchunks = (bytes + kStageChunk - 1) / kStageChunk;
     int slot[kStageSlots];
+    // every buffer is free on the host side here (earlier downloads have copied theirs out): start the
+    // rotation at a buffer that is already pinned instead of pinning the next one
+    for (int i = 0; i < kStageSlots; i++)
+        if (s->stage[i]) {
+            s->stage_next = (unsigned)i;
+            break;
+        }
     // keep up to kStageSlots - 1 DMAs in flight ahead of the host copy
     size_t issued = 0;
     auto issue = [&]() -> int {
