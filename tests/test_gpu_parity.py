@@ -251,3 +251,38 @@ print('callbacks ok')
 """
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True)
     assert r.returncode == 0 and 'callbacks ok' in r.stdout, r.stdout + r.stderr
+
+
+_TMA_CHILD = r'''
+import sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+from jpeg2png_b200 import abi, synth
+from tests import helpers as H
+checker = 'ref' if H.have_ref() else 'oracle'
+cases = [
+    (712, 384, 40, '4:4:4', [0, 1, 2], 0.3, [0.001, 0.002, 0.0], 20),   # 89 blocks wide: ragged last warp tile, one plane without the DCT-distance term
+    (520, 264, 75, '4:2:0', [0, 1, 2], 0.3, [0.001] * 3, 25),          # luma through the TMA kernel, chroma through the 2x2 tile kernel
+    (1920, 1080, 10, '4:2:0', [0], 0.3, [0.001], 12),                  # coefficient grid shorter than the frame (resample build), one plane
+    (64, 64, 90, '4:4:4', [0, 1, 2], 0.0, [0.0] * 3, 10),              # TV only, no DCT-distance term at all
+]
+for w, h, q, ss, channels, weight, pw, iters in cases:
+    img = synth.synth_coefs(w, h, q, ss, seed=4321 + w + h)
+    f = H.decode_planes(img, channels)
+    want = H.run_compute(checker, img, channels, weight, pw, iters, f)
+    got = H.run_compute('product', img, channels, weight, pw, iters, f)
+    H.assert_bit_identical(got, want, f'TMA projection {w}x{h} {ss}')
+print('tma parity ok', len(cases))
+'''
+
+
+def test_tma_projection_matches_oracle(lib):
+    """The opt-in persistent TMA-fed projection kernel (kernels_project_tma.cu: UTMALDG / UTMASTG,
+    J2P_PROJ_TMA=1) against the checker, in a child process because the switch is read once per
+    process.  The default projection kernels are what every other test in this file exercises."""
+    import subprocess
+    import sys
+    env = dict(os.environ, J2P_PROJ_TMA='1')
+    r = subprocess.run([sys.executable, '-c', _TMA_CHILD, H.ROOT], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert 'tma parity ok' in r.stdout

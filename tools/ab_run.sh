@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
-timeout 300 python tools/cli_batch.py 32 > gpurun_out/cli_batch_trace.txt 2>&1; head -2 gpurun_out/cli_batch_trace.txt
-grep "session create" gpurun_out/cli_batch_trace.txt | head -20
-grep "session create" gpurun_out/cli_batch_trace.txt | tail -6
+export J2P_EXPECT_GPU=1
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "tma or callbacks or reset" > gpurun_out/pytest_tma.log 2>&1
+tail -8 gpurun_out/pytest_tma.log
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2
