@@ -7,7 +7,7 @@
 // warp-level 16-byte access touches 32 sectors and uses half of each: the knock-out experiments
 // in profiles/r01_notes.md show that kernel spending 47 us per 4K plane on memory instructions
 // alone (the L1 sector rate), more than the 28 us the fp64 conversions need.  Here a CTA owns a
-// tile of 32 blocks x 1 block (256 x 8 pixels); its 256 threads copy each 8 KB array with
+// tile of 16 blocks x 1 block (128 x 8 pixels); its 128 threads copy each 4 KB array with
 // consecutive lanes on consecutive 16-byte pieces (cp.async, 512 contiguous bytes per warp
 // instruction, every sector used once), into a layout whose 16-byte columns are XOR-swizzled by
 // the row so that the per-row reads of the compute mapping are bank-conflict free.  Results go
@@ -23,11 +23,19 @@
 
 namespace j2p {
 
-constexpr int PT_NT = 256;            // 32 blocks x 8 rows
-constexpr int PT_C4 = 64;             // float4 columns per tile row (256 pixels)
+#ifndef J2P_TILE_BLOCKS
+#define J2P_TILE_BLOCKS 16            // coefficient blocks per CTA tile (16 or 32: the tables and the norm take 96 threads).  Measured at 4K
+                                      // (profiles/r02_ab_gradient_geometry.txt): 16-block tiles in eight 4-warp CTAs per SM 130.1 us, 32-block tiles in
+                                      // four 8-warp CTAs 133.0 us — same resident warps, half as many warps behind each of the two CTA barriers
+#endif
+constexpr int PT_NB = J2P_TILE_BLOCKS;
+constexpr int PT_NT = PT_NB * 8;      // 8 threads per block
+constexpr int PT_C4 = PT_NB * 2;      // float4 columns per tile row
+constexpr int PT_SH = PT_NB == 32 ? 6 : (PT_NB == 16 ? 5 : 7);   // log2(PT_C4)
+static_assert(PT_C4 == 1 << PT_SH, "tile width");
 
 #ifndef J2P_TILE_MIN_CTAS
-#define J2P_TILE_MIN_CTAS 4
+#define J2P_TILE_MIN_CTAS (256 / J2P_TILE_BLOCKS / 2)      // 32 warps per SM either way (64 registers)
 #endif
 // RES: the plane's coefficient grid is smaller than the frame (compute.c:338), e.g. 1080p luma
 template <bool RES>
@@ -43,8 +51,8 @@ __global__ void __launch_bounds__(PT_NT, J2P_TILE_MIN_CTAS) k_project_tile(const
     const PlaneDev &P = F.pl[c];
     const int W = F.W;
     const int bw = P.cw >> 3;
-    const int bx0 = blockIdx.x * 32, by = strip_row_order(F.sync, blockIdx.y, gridDim.y);   // the grid covers real blocks only
-    const int nbx = min(32, bw - bx0);                           // blocks of this tile that exist
+    const int bx0 = blockIdx.x * PT_NB, by = strip_row_order(F.sync, blockIdx.y, gridDim.y);   // the grid covers real blocks only
+    const int nbx = min(PT_NB, bw - bx0);                           // blocks of this tile that exist
     const int valid_c4 = nbx * 2;
     const size_t row0 = (size_t)(by * 8) * W + (size_t)bx0 * 8;  // first pixel of the tile
 
@@ -55,7 +63,7 @@ __global__ void __launch_bounds__(PT_NT, J2P_TILE_MIN_CTAS) k_project_tile(const
     // behind the table loads (20 waves of short-lived CTAs pay their prologue latency in the open).
 #pragma unroll
     for (int i = 0; i < 2; i++) {
-        const int e = tid + PT_NT * i, row = e >> 6, c4 = e & 63;
+        const int e = tid + PT_NT * i, row = e >> PT_SH, c4 = e & (PT_C4 - 1);
         if (c4 < valid_c4) {
             const size_t gi = row0 + (size_t)row * W + (size_t)c4 * 4;
             cp_async16(&sx[row][c4 ^ row], P.x + gi);
@@ -66,7 +74,7 @@ __global__ void __launch_bounds__(PT_NT, J2P_TILE_MIN_CTAS) k_project_tile(const
     pdl_launch_dependents();
 #pragma unroll
     for (int i = 0; i < 2; i++) {
-        const int e = tid + PT_NT * i, row = e >> 6, c4 = e & 63;
+        const int e = tid + PT_NT * i, row = e >> PT_SH, c4 = e & (PT_C4 - 1);
         if (c4 < valid_c4) cp_async16(&sg[row][c4 ^ row], P.g + row0 + (size_t)row * W + (size_t)c4 * 4);
     }
     cp_async_commit();
@@ -193,7 +201,7 @@ __global__ void __launch_bounds__(PT_NT, J2P_TILE_MIN_CTAS) k_project_tile(const
     float *gp0 = P.gp + (size_t)(by * 8) * P.cw + (size_t)bx0 * 8;
 #pragma unroll
     for (int i = 0; i < 2; i++) {
-        const int e = tid + PT_NT * i, row = e >> 6, c4 = e & 63;
+        const int e = tid + PT_NT * i, row = e >> PT_SH, c4 = e & (PT_C4 - 1);
         if (c4 < valid_c4) {
             *reinterpret_cast<float4 *>(P.xp + row0 + (size_t)row * W + (size_t)c4 * 4) = sx[row][c4 ^ row];
             if (use_prob) *reinterpret_cast<float4 *>(gp0 + (size_t)row * P.cw + (size_t)c4 * 4) = sp[row][c4 ^ row];
@@ -207,7 +215,7 @@ __global__ void __launch_bounds__(PT_NT, J2P_TILE_MIN_CTAS) k_project_tile(const
         const bool top = by == 0 && S.has_up, bottom = by == (int)gridDim.y - 1 && S.has_down;
         if (top || bottom) {
             for (int e = tid; e < 4 * PT_C4; e += PT_NT) {                // 2 rows x 64 pieces, top then bottom
-                const int side = e >> 7, r = (e >> 6) & 1, c4 = e & 63;
+                const int side = e >> (PT_SH + 1), r = (e >> PT_SH) & 1, c4 = e & (PT_C4 - 1);
                 if (c4 >= valid_c4 || !(side ? bottom : top)) continue;
                 const int row = side ? 6 + r : r;
                 float *dst = (side ? S.down_dst[c] : S.up_dst[c]) + (size_t)r * W + (size_t)bx0 * 8 + (size_t)c4 * 4;
@@ -257,13 +265,16 @@ static cudaError_t launch_step_uncovered(const FrameDev &F, int c, float factor,
     return cudaGetLastError();
 }
 
+// CTAs of plane P per block row: what calls strip_border_done per side and iteration (session.cu counts them)
+int project_tile_border_units(const PlaneDev &P) { return ((P.cw >> 3) + PT_NB - 1) / PT_NB; }
+
 // F: already restricted to the rows the session owns (launch_project).  Projects planes
 // c .. c+count-1, which must all be 1x1 planes with the same coefficient grid.
 // uncovered_only: the tiles have been projected by the TMA kernel; only the stepped-only pixels remain
 cudaError_t launch_project_tile(const FrameDev &F, int c, int count, float factor, cudaStream_t s, int *nlaunch, bool uncovered_only) {
     const PlaneDev &P = F.pl[c];
     const int bw = P.cw >> 3, bh = P.ch >> 3;
-    const dim3 grid((bw + 31) / 32, bh, count);
+    const dim3 grid((bw + PT_NB - 1) / PT_NB, bh, count);
     cudaError_t e = cudaSuccess;
     if (!uncovered_only) {
         e = P.resample ? launch_chain(k_project_tile<true>, grid, dim3(PT_NT), 0, s, F, c, factor) : launch_chain(k_project_tile<false>, grid, dim3(PT_NT), 0, s, F, c, factor);

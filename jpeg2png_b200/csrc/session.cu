@@ -43,6 +43,7 @@ cudaError_t launch_init_plane(const float *fdata, float *x, float *xp, int W, in
                               cudaStream_t s);
 bool project_tma_enabled();
 int project_tma_border_units(const PlaneDev &P);
+int project_tile_border_units(const PlaneDev &P);
 cudaError_t launch_scanlines(const float *Y, const float *Cb, const float *Cr, int W, int w, int h, int bits, uint8_t *out, cudaStream_t s);
 // kernels_strip.cu: the strip exchanges over peer memory (parameter blocks in kernels.cuh)
 cudaError_t launch_halo_exchange(const HaloPeers &P, unsigned seq, unsigned *ticket, int *err, int wait_for_arrival, cudaStream_t s);
@@ -1093,7 +1094,8 @@ static int p2p_bind(j2p_comm *c, j2p_session *s, const NcclApi *api) {
             fused = fused && tiled && P.cw * P.sw == F.W;
             // units of work per block row that deliver border rows: warp tiles of the TMA kernel, CTA tiles of the cp.async kernels
             if (P.sw == 1 && F.host_maps && project_tma_enabled()) ctas += (unsigned)project_tma_border_units(P);
-            else ctas += (unsigned)(((P.cw >> 3) + (P.sw == 1 ? 31 : 15)) / (P.sw == 1 ? 32 : 16));
+            else if (P.sw == 1) ctas += (unsigned)project_tile_border_units(P);
+            else ctas += (unsigned)(((P.cw >> 3) + 15) / 16);                     // kernels_project_tile22.cu: 16 blocks per CTA tile
         }
         const char *e = getenv("J2P_STRIP_FUSED_HALO");
         if (e && *e == '0') fused = false;
