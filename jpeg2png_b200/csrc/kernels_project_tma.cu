@@ -1,6 +1,14 @@
 // kernels_project_tma.cu — step + projection of full-resolution (1x1) planes as a PERSISTENT,
 // WARP-AUTONOMOUS kernel whose tiles arrive AND leave through the Tensor Memory Accelerator.
 //
+// OPT-IN (J2P_PROJ_TMA=1).  Bit-identical to the default kernel (tests/test_gpu_parity.py runs the
+// parity cases through it) but slower on every frame measured: 158 us against 130 us for the three
+// planes of a 4K frame (profiles/r02_notes.md, r02_ncu_k_project_tma_v3_tma_store_32warps.txt).  An
+// 8-row tile whose swizzle depends on the pixel row is eight TMA boxes per array; the per-box issue
+// cost in the one issuing lane and the per-tile bookkeeping of a persistent loop outweigh the
+// copy instructions TMA saves, and the copy is not what bounds this kernel (the fp64<->fp32
+// conversion pipe and instruction issue are).  Kept as the measured alternative.
+//
 // Arithmetic and thread mapping are those of kernels_project_tile.cu (8 threads per 8x8 block,
 // thread j owns row j, three 2-D transforms through swizzled shared-memory transposes).  What
 // changes is the unit of work and how it travels:
