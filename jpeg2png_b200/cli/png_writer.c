@@ -59,12 +59,28 @@ static int put_chunk(FILE *f, const char *type, const uint8_t *data, size_t len)
 #define J2P_PIECE ((size_t)1 << 20)
 #define J2P_FAIL() do { _Pragma("omp atomic write") failed = 1; } while (0)
 
-/* Compression effort: the reference leaves libpng at zlib level 6.  What must match is the pixels,
- * not the file bytes, and on a GPU the deflate of a multi-megapixel image costs several times the
- * solve it follows (profiles/r01_cli_batch.txt: 170-290 ms per 1080p file against 30 ms).  Images
- * of a megapixel or more are therefore deflated at level 1 (about 4x faster, files ~10-15 % larger);
- * small images keep level 6. */
-static int deflate_level(size_t raw_bytes) { return raw_bytes >= (size_t)3 << 20 ? 1 : 6; }
+/* Compression effort: the reference leaves libpng at zlib level 6 and its default filter heuristics.
+ * What must match is the pixels, not the file bytes, and on a GPU the deflate of a multi-megapixel
+ * image costs several times the solve it follows (profiles/r01_cli_batch.txt: 170-290 ms per 1080p
+ * file against 30 ms).  Images of a megapixel or more are therefore written with the Up filter
+ * (type 2: every byte minus the byte above it — smooth images leave small residuals) and deflated at
+ * level 1 with the run-length strategy, which suits such residuals: on a 1080p frame 72 ms and
+ * 2.9 MB against 166 ms and 4.9 MB for unfiltered scanlines at level 1 (183 ms, 5.0 MB at level 6).
+ * Small images keep unfiltered scanlines at level 6. */
+static int big_image(size_t raw_bytes) { return raw_bytes >= (size_t)3 << 20; }
+static int deflate_level(size_t raw_bytes) { return big_image(raw_bytes) ? 1 : 6; }
+static int deflate_strategy(size_t raw_bytes) { return big_image(raw_bytes) ? Z_RLE : Z_DEFAULT_STRATEGY; }
+
+/* Up filter in place.  Bottom-up, so the row above is still unfiltered when it is subtracted; row 0
+ * keeps filter type 0 (its "row above" is all zeros, Up would leave it unchanged anyway). */
+static void filter_up_in_place(uint8_t *raw, size_t stride, unsigned h) {
+        for (unsigned y = h; y-- > 1;) {
+                uint8_t *cur = raw + (size_t)y * stride;
+                const uint8_t *up = cur - stride;
+                cur[0] = 2;
+                for (size_t i = 1; i < stride; i++) cur[i] = (uint8_t)(cur[i] - up[i]);
+        }
+}
 
 static uint8_t *deflate_pieces(const uint8_t *raw, size_t len, size_t *zlen) {
         const int level = deflate_level(len);
@@ -79,7 +95,7 @@ static uint8_t *deflate_pieces(const uint8_t *raw, size_t len, size_t *zlen) {
                 const size_t off = (size_t)i * J2P_PIECE, n = len - off < J2P_PIECE ? len - off : J2P_PIECE;
                 z_stream zs;
                 memset(&zs, 0, sizeof zs);
-                if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { J2P_FAIL(); continue; }
+                if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, deflate_strategy(len)) != Z_OK) { J2P_FAIL(); continue; }
                 const size_t cap = deflateBound(&zs, (uLong)n) + 64;
                 buf[i] = malloc(cap);
                 if (buf[i]) {
@@ -122,12 +138,14 @@ static uint8_t *deflate_pieces(const uint8_t *raw, size_t len, size_t *zlen) {
         return z;
 }
 
-/* `raw`: h scanlines of 1 + w*3*bits/8 bytes, each starting with its filter-type byte */
-int j2p_write_png_scanlines(FILE *out, unsigned w, unsigned h, unsigned bits, const uint8_t *raw) {
+/* `raw`: h UNFILTERED scanlines of 1 + w*3*bits/8 bytes, each starting with filter-type byte 0.
+ * Large images are filtered in place (the buffer is the caller's scratch). */
+int j2p_write_png_scanlines(FILE *out, unsigned w, unsigned h, unsigned bits, uint8_t *raw) {
         if (bits != 8 && bits != 16) return -1;
         const size_t stride = (size_t)w * 3 * (bits / 8) + 1;
         size_t zlen = 0;
         uint8_t *z = NULL;
+        if (big_image(stride * h)) filter_up_in_place(raw, stride, h);
         if (stride * h > 2 * J2P_PIECE) {
                 z = deflate_pieces(raw, stride * h, &zlen);
         } else {

@@ -15,8 +15,9 @@ void j2p_ycc_to_rgb(unsigned w, unsigned h, unsigned bits, const float *y, unsig
 int j2p_write_png(FILE *out, unsigned w, unsigned h, unsigned bits, const float *y, unsigned y_stride, const float *cb,
                   unsigned cb_stride, const float *cr, unsigned cr_stride);
 
-/* Same container from finished scanlines (h rows of 1 + w*3*bits/8 bytes, filter byte first): what
- * j2p_session_download_scanlines() delivers from the device. */
-int j2p_write_png_scanlines(FILE *out, unsigned w, unsigned h, unsigned bits, const uint8_t *raw);
+/* Same container from unfiltered scanlines (h rows of 1 + w*3*bits/8 bytes, filter byte 0 first):
+ * what j2p_session_download_scanlines() delivers from the device.  `raw` is scratch: large images
+ * are filtered in place before they are deflated. */
+int j2p_write_png_scanlines(FILE *out, unsigned w, unsigned h, unsigned bits, uint8_t *raw);
 
 #endif
